@@ -193,7 +193,7 @@ ora_sketch_t *ora_sketch_contigs(const char *const *seqs, const int64_t *lens, i
     u64vec seeds = {0}, markers = {0};
     uint32_t off = 0;
     for (int i = 0; i < n; i++) {
-        if (lens[i] < p->min_contig_len) continue;
+        if (lens[i] < p->min_contig_len || lens[i] <= 0) continue;
         int c = s->n_contigs++;
         s->contig_len[c] = lens[i];
         s->contig_off[c] = off;
@@ -259,7 +259,7 @@ ora_sketch_t *ora_sketch_file(const char *path, const ora_params_t *p) {
     free(s->first_name);
     s->first_name = NULL;
     for (int r = 0; r < nrec; r++) {
-        if (!s->first_name && lens[r] >= p->min_contig_len) s->first_name = strdup(names[r]);
+        if (!s->first_name && lens[r] >= p->min_contig_len && lens[r] > 0) s->first_name = strdup(names[r]);
         free(names[r]);
     }
     if (!s->first_name) s->first_name = strdup("");

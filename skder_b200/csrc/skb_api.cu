@@ -1,0 +1,942 @@
+// C-ABI of libskani_b200.so (include/skani_b200.h): context, device buffers, kernel launches.
+// No CPU fallback anywhere: every compute entry point launches the sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "skb_ani.cuh"
+#include "skb_common.cuh"
+#include "skb_index.cuh"
+#include "skb_sketch.cuh"
+
+using namespace skb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaFail {
+    std::string msg;
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            throw CudaFail{std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                           std::to_string(__LINE__) + ")"};                                               \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow to at least n elements, keeping the first `keep` elements
+    void reserve(size_t n, size_t keep, cudaStream_t st) {
+        if (n <= cap) return;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        CK(cudaMalloc(&q, ncap * sizeof(T)));
+        if (p && keep) CK(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = q;
+        cap = ncap;
+    }
+    void upload(const std::vector<T> &h, cudaStream_t st) {
+        reserve(std::max<size_t>(h.size(), 1), 0, st);
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+struct skb_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    skb_params prm;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    bool ani_attr_set = false;
+
+    // ---- sketch DB (host metadata)
+    std::vector<uint64_t> h_seed_off{0};   // [n+1]
+    std::vector<uint64_t> h_total_len;     // [n]
+    std::vector<uint32_t> h_ctg_off{0};    // [n+1]
+    std::vector<uint32_t> h_ctg_len;       // kept contig lengths
+    uint64_t n_mkeys = 0;                  // raw marker keys so far
+    // ---- device arrays
+    DevBuf<uint64_t> d_seeds, d_mkeys;
+    // built by skb_index
+    bool indexed = false;
+    int32_t n_indexed = 0;
+    DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
+    DevBuf<uint8_t> d_tab_bits;
+    DevBuf<uint32_t> d_chunk_begin, d_chunk_start, d_chunk_len, d_chunk_off, d_ctg_pstart, d_ctg_len, d_ctg_off,
+        d_marker_cnt;
+    std::vector<uint64_t> h_marker_off;    // [n+1]
+    std::vector<uint32_t> h_chunk_off;     // [n+1]
+    uint64_t n_inv = 0;
+    // scratch
+    DevBuf<unsigned char> d_tmp;
+    DevBuf<int> d_counter;
+
+    int32_t n() const { return (int32_t)h_total_len.size(); }
+    DbView view() const {
+        DbView v;
+        v.n_genomes = n_indexed;
+        v.seeds = d_seeds.p;
+        v.g_seed_off = d_seed_off.p;
+        v.tab = d_tab.p;
+        v.g_tab_off = d_tab_off.p;
+        v.g_tab_bits = d_tab_bits.p;
+        v.chunk_begin = d_chunk_begin.p;
+        v.chunk_start = d_chunk_start.p;
+        v.chunk_len = d_chunk_len.p;
+        v.g_chunk_off = d_chunk_off.p;
+        v.ctg_pstart = d_ctg_pstart.p;
+        v.ctg_len = d_ctg_len.p;
+        v.g_ctg_off = d_ctg_off.p;
+        v.g_total_len = d_total_len.p;
+        v.markers = d_markers.p;
+        v.g_marker_off = d_marker_off.p;
+        v.inv_keys = d_inv.p;
+        v.n_inv = (int64_t)n_inv;
+        return v;
+    }
+    AniParams ani_params() const {
+        AniParams a;
+        a.band_bp = prm.band_bp;
+        a.max_gap = prm.max_gap;
+        a.anchor_score = prm.anchor_score;
+        a.min_anchors = prm.min_anchors;
+        a.min_score = prm.min_score;
+        a.max_mult = prm.max_mult;
+        a.max_chunk_chains = prm.max_chunk_chains;
+        a.ovl_num = prm.ovl_num;
+        a.ovl_den = prm.ovl_den;
+        a.span_ext = prm.span_ext;
+        a.min_chunk_seeds = prm.min_chunk_seeds;
+        a.debias_a = prm.debias_a;
+        a.debias_g = prm.debias_g;
+        return a;
+    }
+};
+
+namespace {
+
+template <typename F>
+int guarded(skb_ctx *ctx, F &&f) {
+    if (!ctx) return SKB_EINVAL;
+    try {
+        CK(cudaSetDevice(ctx->device));
+        return f();
+    } catch (const CudaFail &e) {
+        ctx->err = e.msg;
+        return SKB_ECUDA;
+    } catch (const std::bad_alloc &) {
+        ctx->err = "host out of memory";
+        return SKB_ENOMEM;
+    } catch (const std::exception &e) {
+        ctx->err = e.what();
+        return SKB_EINVAL;
+    }
+}
+
+int fail(skb_ctx *ctx, int code, const std::string &m) {
+    ctx->err = m;
+    return code;
+}
+
+void exclusive_scan_u32(skb_ctx *c, const uint32_t *in, uint32_t *out, size_t n) {
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, c->st));
+    c->d_tmp.reserve(bytes + 16, 0, c->st);
+    CK(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, bytes, in, out, (int)n, c->st));
+    c->launches += 2;
+}
+
+void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int end_bit = 64) {
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int64_t)n, 0, end_bit, c->st));
+    c->d_tmp.reserve(bytes + 16, 0, c->st);
+    CK(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, bytes, in, out, (int64_t)n, 0, end_bit, c->st));
+    c->launches += (end_bit + 7) / 8 + 1;
+}
+
+// ---- sketch a batch of packed genomes [g0, g1) of the caller's list ------------------------------
+void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1) {
+    const int32_t nb = g1 - g0;
+    std::vector<uint64_t> word_off(nb + 1, 0), nbases(nb), ctg_start;
+    std::vector<uint32_t> ctg_off(nb + 1, 0), tile_off(nb + 1, 0);
+    for (int32_t i = 0; i < nb; i++) {
+        const skb_packed *p = gen[g0 + i];
+        word_off[i + 1] = word_off[i] + (uint64_t)p->n_words;
+        nbases[i] = (uint64_t)p->n_bases;
+        uint64_t s = 0;
+        for (int32_t k = 0; k < p->n_contigs; k++) {
+            ctg_start.push_back(s);
+            s += (uint64_t)p->contig_lens[k];
+        }
+        if (p->n_contigs == 0) ctg_start.push_back(0);  // keep one entry so the kernel's search is well-defined
+        ctg_off[i + 1] = (uint32_t)ctg_start.size();
+        tile_off[i + 1] = tile_off[i] + (uint32_t)std::max<uint64_t>(1, (nbases[i] + SK_TILE_BASES - 1) / SK_TILE_BASES);
+    }
+    const uint32_t n_tiles = tile_off[nb];
+    const size_t n_warps = (size_t)n_tiles * SK_WARPS;
+    DevBuf<uint64_t> d_packed, d_word_off, d_nbases, d_ctg_start;
+    DevBuf<uint32_t> d_ctg_off, d_tile_off, d_cnt_s, d_cnt_m, d_off_s, d_off_m;
+    d_packed.reserve(word_off[nb] + 2, 0, c->st);
+    for (int32_t i = 0; i < nb; i++)
+        CK(cudaMemcpyAsync(d_packed.p + word_off[i], gen[g0 + i]->words, (size_t)gen[g0 + i]->n_words * 8,
+                           cudaMemcpyHostToDevice, c->st));
+    d_word_off.upload(word_off, c->st);
+    d_nbases.upload(nbases, c->st);
+    d_ctg_start.upload(ctg_start, c->st);
+    d_ctg_off.upload(ctg_off, c->st);
+    d_tile_off.upload(tile_off, c->st);
+    d_cnt_s.reserve(n_warps + 1, 0, c->st);
+    d_cnt_m.reserve(n_warps + 1, 0, c->st);
+    d_off_s.reserve(n_warps + 1, 0, c->st);
+    d_off_m.reserve(n_warps + 1, 0, c->st);
+    CK(cudaMemsetAsync(d_cnt_s.p + n_warps, 0, 4, c->st));
+    CK(cudaMemsetAsync(d_cnt_m.p + n_warps, 0, 4, c->st));
+    SketchBatch b;
+    b.packed = d_packed.p;
+    b.g_word_off = d_word_off.p;
+    b.g_nbases = d_nbases.p;
+    b.g_ctg_off = d_ctg_off.p;
+    b.ctg_start = d_ctg_start.p;
+    b.tile_off = d_tile_off.p;
+    b.n = nb;
+    b.first_gid = (uint32_t)c->n();
+    sketch_kernel<false><<<n_tiles, SK_THREADS, 0, c->st>>>(b, d_cnt_s.p, d_cnt_m.p, nullptr, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+    c->launches++;
+    exclusive_scan_u32(c, d_cnt_s.p, d_off_s.p, n_warps + 1);
+    exclusive_scan_u32(c, d_cnt_m.p, d_off_m.p, n_warps + 1);
+    // per-genome seed offsets = scanned offsets at genome tile boundaries
+    std::vector<uint32_t> h_off_s(nb + 1);
+    uint32_t tot_m = 0;
+    for (int32_t i = 0; i <= nb; i++)
+        CK(cudaMemcpyAsync(&h_off_s[i], d_off_s.p + (size_t)tile_off[i] * SK_WARPS, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&tot_m, d_off_m.p + n_warps, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t cur_seeds = c->h_seed_off.back();
+    const uint64_t tot_s = h_off_s[nb];
+    c->d_seeds.reserve(cur_seeds + tot_s + 1, cur_seeds, c->st);
+    c->d_mkeys.reserve(c->n_mkeys + tot_m + 1, c->n_mkeys, c->st);
+    sketch_kernel<true><<<n_tiles, SK_THREADS, 0, c->st>>>(b, nullptr, nullptr, d_off_s.p, d_off_m.p,
+                                                           c->d_seeds.p + cur_seeds, c->d_mkeys.p + c->n_mkeys);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaStreamSynchronize(c->st));  // batch-local buffers die here
+    for (int32_t i = 0; i < nb; i++) {
+        const skb_packed *p = gen[g0 + i];
+        c->h_seed_off.push_back(cur_seeds + h_off_s[i + 1]);
+        c->h_total_len.push_back((uint64_t)p->n_bases);
+        for (int32_t k = 0; k < p->n_contigs; k++) c->h_ctg_len.push_back((uint32_t)p->contig_lens[k]);
+        c->h_ctg_off.push_back((uint32_t)c->h_ctg_len.size());
+    }
+    c->n_mkeys += tot_m;
+    c->indexed = false;
+}
+
+// ---- ANI over a device-resident pair list --------------------------------------------------------
+void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, PairOut *d_out) {
+    if (n_pairs == 0) return;
+    c->d_counter.reserve(4, 0, c->st);
+    CK(cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), c->st));
+    if (!c->ani_attr_set) {
+        CK(cudaFuncSetAttribute(ani_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ANI_SMEM_BYTES));
+        c->ani_attr_set = true;
+    }
+    const int grid = (int)std::min<int64_t>(n_pairs, c->sm_count);
+    ani_pair_kernel<<<grid, ANI_THREADS, ANI_SMEM_BYTES, c->st>>>(c->view(), c->ani_params(), d_pairs, n_pairs, d_out,
+                                                                  c->d_counter.p);
+    CK(cudaGetLastError());
+    c->launches++;
+}
+
+struct EdgeRun {
+    std::vector<skb_edge> edges;
+    int64_t n_screened = 0;
+    float ms_screen = 0, ms_ani = 0;
+};
+
+// pairs on device -> ANI -> compacted edges on host
+void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, double min_af_pct, EdgeRun &run,
+                    cudaEvent_t ev_mid, cudaEvent_t ev_end) {
+    DevBuf<PairOut> d_out;
+    DevBuf<skb_edge> d_edges;
+    DevBuf<unsigned long long> d_n;
+    d_n.reserve(1, 0, c->st);
+    CK(cudaMemsetAsync(d_n.p, 0, 8, c->st));
+    CK(cudaEventRecord(ev_mid, c->st));
+    unsigned long long ne = 0;
+    if (n_pairs > 0) {
+        d_out.reserve((size_t)n_pairs, 0, c->st);
+        d_edges.reserve((size_t)n_pairs, 0, c->st);
+        run_ani(c, d_pairs, n_pairs, d_out.p);
+        edge_compact_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(d_pairs, d_out.p, n_pairs,
+                                                                            min_af_pct / 100.0, d_edges.p, d_n.p);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    CK(cudaEventRecord(ev_end, c->st));
+    CK(cudaMemcpyAsync(&ne, d_n.p, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    run.edges.resize((size_t)ne);
+    if (ne) CK(cudaMemcpy(run.edges.data(), d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost));
+    std::sort(run.edges.begin(), run.edges.end(), [](const skb_edge &x, const skb_edge &y) {
+        return x.a != y.a ? x.a < y.a : x.b < y.b;
+    });
+}
+
+int emit_edges(skb_ctx *c, EdgeRun &run, skb_edge **edges, int64_t *n_edges) {
+    *n_edges = (int64_t)run.edges.size();
+    *edges = (skb_edge *)std::malloc(std::max<size_t>(1, run.edges.size()) * sizeof(skb_edge));
+    if (!*edges) return fail(c, SKB_ENOMEM, "host out of memory for edges");
+    if (!run.edges.empty()) std::memcpy(*edges, run.edges.data(), run.edges.size() * sizeof(skb_edge));
+    return SKB_OK;
+}
+
+bool write_all(FILE *f, const void *p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+bool read_all(FILE *f, void *p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+
+}  // namespace
+
+extern "C" {
+
+void skb_default_params(skb_params *p) {
+    p->min_contig_len = 500;
+    p->chunk_len = 20000;
+    p->band_bp = 2500;
+    p->max_gap = 300;
+    p->anchor_score = 20;
+    p->min_anchors = 3;
+    p->min_score = 45;
+    p->max_mult = 8;
+    p->max_chunk_chains = 4;
+    p->ovl_num = 1;
+    p->ovl_den = 2;
+    p->span_ext = 150;
+    p->min_chunk_seeds = 1;
+    p->debias_a = 1.49745019;
+    p->debias_g = 0.8781001;
+}
+
+int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
+    if (!out) return SKB_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (libskani_b200 has no CPU path)";
+        return SKB_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return SKB_EINVAL;
+    }
+    skb_ctx *c = new skb_ctx();
+    c->device = device;
+    if (params)
+        c->prm = *params;
+    else
+        skb_default_params(&c->prm);
+    const skb_params &p = c->prm;
+    if (p.max_mult < 1 || p.max_mult > STAGE || (p.max_mult & (p.max_mult - 1)) || p.max_chunk_chains < 1 ||
+        p.max_chunk_chains > 8 || p.band_bp >= (int32_t)CONTIG_PAD || p.band_bp < 1 || p.chunk_len < 64 ||
+        p.chunk_len > 32767 || p.anchor_score < 1 || p.anchor_score > 20 || p.ovl_den < 1) {
+        g_create_error = "parameter outside the range the kernels support";
+        delete c;
+        return SKB_EINVAL;
+    }
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+        delete c;
+        return SKB_ECUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only";
+        delete c;
+        return SKB_ECUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return SKB_OK;
+}
+
+void skb_destroy(skb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) {
+        cudaStreamSynchronize(ctx->st);
+        cudaStreamDestroy(ctx->st);
+    }
+    delete ctx;
+}
+
+const char *skb_last_error(const skb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int32_t skb_n_genomes(const skb_ctx *ctx) { return ctx ? ctx->n() : 0; }
+int64_t skb_launch_count(const skb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *skb_stream(const skb_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
+void skb_free(void *p) { std::free(p); }
+
+int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
+    return guarded(ctx, [&]() -> int {
+        if (n < 0 || (n > 0 && !genomes)) return fail(ctx, SKB_EINVAL, "bad genome list");
+        if ((uint64_t)ctx->n() + (uint64_t)n >= GID_MASK) return fail(ctx, SKB_ELIMIT, "too many genomes (22-bit ids)");
+        for (int32_t i = 0; i < n; i++) {
+            const skb_packed *p = genomes[i];
+            if (!p || !p->words || (p->n_words & 1) || p->n_words * 32 < p->n_bases)
+                return fail(ctx, SKB_EINVAL, "genome " + std::to_string(i) + ": malformed packed buffer");
+            uint64_t s = 0;
+            for (int32_t k = 0; k < p->n_contigs; k++) s += (uint64_t)p->contig_lens[k];
+            if (s != (uint64_t)p->n_bases) return fail(ctx, SKB_EINVAL, "contig lengths do not sum to n_bases");
+            if ((uint64_t)p->n_bases + (uint64_t)p->n_contigs * CONTIG_PAD >= (1ull << 31))
+                return fail(ctx, SKB_ELIMIT, "genome too large for 31-bit padded coordinates");
+        }
+        // batches of <= 1 Gi bases: per-batch seed/marker totals stay far below 2^32
+        int32_t g0 = 0;
+        while (g0 < n) {
+            uint64_t bases = 0;
+            int32_t g1 = g0;
+            while (g1 < n && (g1 == g0 || bases + (uint64_t)genomes[g1]->n_bases <= (1ull << 30))) {
+                bases += (uint64_t)genomes[g1]->n_bases;
+                g1++;
+            }
+            sketch_batch(ctx, genomes, g0, g1);
+            g0 = g1;
+        }
+        return SKB_OK;
+    });
+}
+
+int skb_index(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        const int32_t n = c->n();
+        if (n == 0) return fail(c, SKB_ESTATE, "no genomes added");
+        const uint64_t n_seeds = c->h_seed_off.back();
+        // ---- host-side tables: seed hash sizes, contigs in padded coordinates, chunks
+        std::vector<uint64_t> tab_off(n + 1, 0);
+        std::vector<uint8_t> tab_bits(n);
+        std::vector<uint32_t> ctg_pstart(c->h_ctg_len.size()), chunk_start, chunk_len;
+        c->h_chunk_off.assign(n + 1, 0);
+        for (int32_t g = 0; g < n; g++) {
+            const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
+            int bits = 1;
+            while ((1ull << bits) < 2 * ns + 2) bits++;
+            if (bits > 31) return fail(c, SKB_ELIMIT, "genome has too many seeds");
+            tab_bits[g] = (uint8_t)bits;
+            tab_off[g + 1] = tab_off[g] + (1ull << bits);
+            uint32_t off = 0;
+            for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
+                ctg_pstart[k] = off;
+                const uint32_t len = c->h_ctg_len[k];
+                for (uint32_t st = 0; st < len; st += (uint32_t)c->prm.chunk_len) {
+                    chunk_start.push_back(off + st);
+                    chunk_len.push_back(std::min<uint32_t>((uint32_t)c->prm.chunk_len, len - st));
+                }
+                off += len + CONTIG_PAD;
+            }
+            c->h_chunk_off[g + 1] = (uint32_t)chunk_start.size();
+        }
+        c->d_seed_off.upload(c->h_seed_off, c->st);
+        c->d_tab_off.upload(tab_off, c->st);
+        c->d_tab_bits.upload(tab_bits, c->st);
+        c->d_total_len.upload(c->h_total_len, c->st);
+        c->d_ctg_pstart.upload(ctg_pstart, c->st);
+        c->d_ctg_len.upload(c->h_ctg_len, c->st);
+        c->d_ctg_off.upload(c->h_ctg_off, c->st);
+        c->d_chunk_start.upload(chunk_start, c->st);
+        c->d_chunk_len.upload(chunk_len, c->st);
+        c->d_chunk_off.upload(c->h_chunk_off, c->st);
+        // ---- K2: seed hash indices + repeat flags + chunk_begin
+        c->d_tab.reserve(tab_off[n], 0, c->st);
+        CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
+        if (n_seeds) {
+            tab_insert_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n,
+                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_bits.p);
+            CK(cudaGetLastError());
+            rep_flag_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n, c->d_tab.p,
+                                                                  c->d_tab_off.p, c->d_tab_bits.p, c->prm.max_mult);
+            CK(cudaGetLastError());
+            c->launches += 2;
+        }
+        const uint32_t n_entries = (uint32_t)chunk_start.size() + (uint32_t)n;
+        c->d_chunk_begin.reserve(n_entries, 0, c->st);
+        chunk_begin_kernel<<<nblk(n_entries, 256), 256, 0, c->st>>>(c->d_seeds.p, c->d_seed_off.p, c->d_chunk_off.p, n,
+                                                                   c->d_chunk_start.p, c->d_chunk_begin.p, n_entries);
+        CK(cudaGetLastError());
+        c->launches++;
+        // ---- markers: sort raw keys, unique -> inverted index; per-genome counts; per-genome lists
+        c->d_marker_cnt.reserve((size_t)n, 0, c->st);
+        CK(cudaMemsetAsync(c->d_marker_cnt.p, 0, (size_t)n * 4, c->st));
+        c->n_inv = 0;
+        c->h_marker_off.assign(n + 1, 0);
+        if (c->n_mkeys) {
+            if (c->n_mkeys >= (1ull << 32)) return fail(c, SKB_ELIMIT, "too many marker keys");
+            DevBuf<uint64_t> d_sorted;
+            DevBuf<uint32_t> d_flag, d_pos;
+            d_sorted.reserve(c->n_mkeys, 0, c->st);
+            d_flag.reserve(c->n_mkeys + 1, 0, c->st);
+            d_pos.reserve(c->n_mkeys + 1, 0, c->st);
+            sort_keys_u64(c, c->d_mkeys.p, d_sorted.p, c->n_mkeys);
+            unique_flag_kernel<<<nblk(c->n_mkeys, 256), 256, 0, c->st>>>(d_sorted.p, c->n_mkeys, d_flag.p);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_flag.p + c->n_mkeys, 0, 4, c->st));
+            exclusive_scan_u32(c, d_flag.p, d_pos.p, c->n_mkeys + 1);
+            uint32_t nu = 0;
+            CK(cudaMemcpyAsync(&nu, d_pos.p + c->n_mkeys, 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            c->n_inv = nu;
+            c->d_inv.reserve(nu + 1, 0, c->st);
+            unique_scatter_kernel<<<nblk(c->n_mkeys, 256), 256, 0, c->st>>>(d_sorted.p, c->n_mkeys, d_flag.p, d_pos.p,
+                                                                           c->d_inv.p, c->d_marker_cnt.p);
+            CK(cudaGetLastError());
+            c->launches += 2;
+            // per-genome sorted lists: swap key halves, sort again, strip ids
+            c->d_markers.reserve(nu + 1, 0, c->st);
+            swap_key_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_inv.p, nu, d_sorted.p);
+            CK(cudaGetLastError());
+            sort_keys_u64(c, d_sorted.p, c->d_markers.p, nu);
+            strip_gid_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_markers.p, nu);
+            CK(cudaGetLastError());
+            c->launches += 2;
+            std::vector<uint32_t> cnt(n);
+            CK(cudaMemcpyAsync(cnt.data(), c->d_marker_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (int32_t g = 0; g < n; g++) c->h_marker_off[g + 1] = c->h_marker_off[g] + cnt[g];
+        }
+        c->d_marker_off.upload(c->h_marker_off, c->st);
+        CK(cudaStreamSynchronize(c->st));
+        c->n_indexed = n;
+        c->indexed = true;
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_sizes(skb_ctx *ctx, int32_t g, int64_t *n_seeds, int64_t *n_markers, int32_t *n_chunks,
+                     int64_t *total_len) {
+    if (!ctx) return SKB_EINVAL;
+    if (g < 0 || g >= ctx->n()) return fail(ctx, SKB_EINVAL, "genome id out of range");
+    if (n_seeds) *n_seeds = (int64_t)(ctx->h_seed_off[g + 1] - ctx->h_seed_off[g]);
+    if (total_len) *total_len = (int64_t)ctx->h_total_len[g];
+    if (n_markers || n_chunks) {
+        if (!ctx->indexed || g >= ctx->n_indexed) return fail(ctx, SKB_ESTATE, "call skb_index first");
+        if (n_markers) *n_markers = (int64_t)(ctx->h_marker_off[g + 1] - ctx->h_marker_off[g]);
+        if (n_chunks) *n_chunks = (int32_t)(ctx->h_chunk_off[g + 1] - ctx->h_chunk_off[g]);
+    }
+    return SKB_OK;
+}
+
+int skb_get_seeds(skb_ctx *ctx, int32_t g, uint64_t *out) {
+    return guarded(ctx, [&]() -> int {
+        if (g < 0 || g >= ctx->n() || !out) return fail(ctx, SKB_EINVAL, "bad arguments");
+        const uint64_t a = ctx->h_seed_off[g], b = ctx->h_seed_off[g + 1];
+        CK(cudaStreamSynchronize(ctx->st));
+        if (b > a) CK(cudaMemcpy(out, ctx->d_seeds.p + a, (b - a) * 8, cudaMemcpyDeviceToHost));
+        return SKB_OK;
+    });
+}
+
+int skb_get_markers(skb_ctx *ctx, int32_t g, uint64_t *out) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->indexed || g < 0 || g >= ctx->n_indexed || !out) return fail(ctx, SKB_ESTATE, "not indexed / bad id");
+        const uint64_t a = ctx->h_marker_off[g], b = ctx->h_marker_off[g + 1];
+        CK(cudaStreamSynchronize(ctx->st));
+        if (b > a) CK(cudaMemcpy(out, ctx->d_markers.p + a, (b - a) * 8, cudaMemcpyDeviceToHost));
+        return SKB_OK;
+    });
+}
+
+int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t part, int32_t n_parts,
+                 skb_edge **edges, int64_t *n_edges, skb_stats *stats) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!edges || !n_edges || n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
+        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        const uint32_t n = (uint32_t)c->n_indexed;
+        const int64_t launches0 = c->launches;
+        cudaEvent_t e0, e1, e2;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventCreate(&e2));
+        CK(cudaEventRecord(e0, c->st));
+        const uint32_t rows_local = (n > (uint32_t)part) ? (n - 1 - (uint32_t)part) / (uint32_t)n_parts + 1 : 0;
+        int64_t pairs_total = 0;
+        for (uint32_t a = (uint32_t)part; a < n; a += (uint32_t)n_parts) pairs_total += n - 1 - a;
+        DevBuf<uint32_t> d_cnt;
+        DevBuf<unsigned long long> d_pairs, d_pairs_sorted, d_np;
+        d_np.reserve(1, 0, c->st);
+        CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
+        const double scale = screen_pct > 0.0 ? std::pow(screen_pct / 100.0, (double)K_MARKER) : 0.0;
+        const uint64_t cells = (uint64_t)rows_local * n;
+        unsigned long long np = 0;
+        if (cells) {
+            d_cnt.reserve(cells, 0, c->st);
+            if (scale > 0.0) {
+                CK(cudaMemsetAsync(d_cnt.p, 0, cells * 4, c->st));
+                if (c->n_inv) {
+                    screen_runs_kernel<<<nblk(c->n_inv, 256), 256, 0, c->st>>>(c->d_inv.p, c->n_inv, d_cnt.p, n, part,
+                                                                              n_parts);
+                    CK(cudaGetLastError());
+                    c->launches++;
+                }
+            }
+            // two passes over the count matrix: count survivors, then write them
+            screen_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, n, rows_local, part, n_parts,
+                                                                      c->d_marker_cnt.p, scale, nullptr, d_np.p, 0ull);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaMemcpyAsync(&np, d_np.p, 8, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            if (np) {
+                d_pairs.reserve(np, 0, c->st);
+                d_pairs_sorted.reserve(np, 0, c->st);
+                CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
+                screen_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, n, rows_local, part, n_parts,
+                                                                          c->d_marker_cnt.p, scale, d_pairs.p, d_np.p,
+                                                                          np);
+                CK(cudaGetLastError());
+                c->launches++;
+                sort_keys_u64(c, (const uint64_t *)d_pairs.p, (uint64_t *)d_pairs_sorted.p, np);
+            }
+        }
+        EdgeRun run;
+        run.n_screened = (int64_t)np;
+        pairs_to_edges(c, d_pairs_sorted.p, (int64_t)np, min_af_pct, run, e1, e2);
+        float ms01 = 0, ms12 = 0;
+        CK(cudaEventElapsedTime(&ms01, e0, e1));
+        CK(cudaEventElapsedTime(&ms12, e1, e2));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaEventDestroy(e2);
+        if (stats) {
+            stats->n_pairs_total = pairs_total;
+            stats->n_pairs_screened = (int64_t)np;
+            stats->n_edges = (int64_t)run.edges.size();
+            stats->ms_screen = ms01;
+            stats->ms_ani = ms12;
+            stats->ms_total = ms01 + ms12;
+            stats->launches = c->launches - launches0;
+        }
+        return emit_edges(c, run, edges, n_edges);
+    });
+}
+
+int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *queries, int32_t n_queries,
+             double screen_pct, double min_af_pct, skb_edge **edges, int64_t *n_edges, skb_stats *stats) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!edges || !n_edges || n_refs < 0 || n_queries < 0 || (n_refs && !refs) || (n_queries && !queries))
+            return fail(c, SKB_EINVAL, "bad arguments");
+        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        const int32_t n = c->n_indexed;
+        const int64_t launches0 = c->launches;
+        std::vector<int32_t> ref_slot(n, -1);
+        for (int32_t i = 0; i < n_refs; i++) {
+            if (refs[i] < 0 || refs[i] >= n) return fail(c, SKB_EINVAL, "reference id out of range");
+            if (ref_slot[refs[i]] >= 0) return fail(c, SKB_EINVAL, "duplicate reference id");
+            ref_slot[refs[i]] = i;
+        }
+        std::vector<uint64_t> qpref(n_queries + 1, 0);
+        for (int32_t i = 0; i < n_queries; i++) {
+            if (queries[i] < 0 || queries[i] >= n) return fail(c, SKB_EINVAL, "query id out of range");
+            qpref[i + 1] = qpref[i] + (c->h_marker_off[queries[i] + 1] - c->h_marker_off[queries[i]]);
+        }
+        cudaEvent_t e0, e1, e2;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventCreate(&e2));
+        CK(cudaEventRecord(e0, c->st));
+        DevBuf<int32_t> d_refs, d_queries, d_slot;
+        DevBuf<uint64_t> d_qpref;
+        DevBuf<uint32_t> d_cnt;
+        DevBuf<unsigned long long> d_pairs, d_pairs_sorted, d_np;
+        const uint64_t cells = (uint64_t)n_refs * (uint64_t)n_queries;
+        unsigned long long np = 0;
+        d_np.reserve(1, 0, c->st);
+        CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
+        const double scale = screen_pct > 0.0 ? std::pow(screen_pct / 100.0, (double)K_MARKER) : 0.0;
+        if (cells) {
+            d_refs.upload(std::vector<int32_t>(refs, refs + n_refs), c->st);
+            d_queries.upload(std::vector<int32_t>(queries, queries + n_queries), c->st);
+            d_slot.upload(ref_slot, c->st);
+            d_qpref.upload(qpref, c->st);
+            d_cnt.reserve(cells, 0, c->st);
+            if (scale > 0.0) {
+                CK(cudaMemsetAsync(d_cnt.p, 0, cells * 4, c->st));
+                if (qpref[n_queries] && c->n_inv) {
+                    screen_rect_kernel<<<nblk(qpref[n_queries], 256), 256, 0, c->st>>>(
+                        c->d_inv.p, c->n_inv, c->d_markers.p, c->d_marker_off.p, d_queries.p, n_queries, d_qpref.p,
+                        d_slot.p, d_cnt.p, (uint32_t)n_refs);
+                    CK(cudaGetLastError());
+                    c->launches++;
+                }
+            }
+            screen_rect_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, d_refs.p, (uint32_t)n_refs,
+                                                                           d_queries.p, (uint32_t)n_queries,
+                                                                           c->d_marker_cnt.p, scale, nullptr, d_np.p, 0ull);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaMemcpyAsync(&np, d_np.p, 8, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            if (np) {
+                d_pairs.reserve(np, 0, c->st);
+                d_pairs_sorted.reserve(np, 0, c->st);
+                CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
+                screen_rect_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(
+                    d_cnt.p, d_refs.p, (uint32_t)n_refs, d_queries.p, (uint32_t)n_queries, c->d_marker_cnt.p, scale,
+                    d_pairs.p, d_np.p, np);
+                CK(cudaGetLastError());
+                c->launches++;
+                sort_keys_u64(c, (const uint64_t *)d_pairs.p, (uint64_t *)d_pairs_sorted.p, np);
+            }
+        }
+        EdgeRun run;
+        pairs_to_edges(c, d_pairs_sorted.p, (int64_t)np, min_af_pct, run, e1, e2);
+        float ms01 = 0, ms12 = 0;
+        CK(cudaEventElapsedTime(&ms01, e0, e1));
+        CK(cudaEventElapsedTime(&ms12, e1, e2));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaEventDestroy(e2);
+        if (stats) {
+            stats->n_pairs_total = (int64_t)cells;
+            stats->n_pairs_screened = (int64_t)np;
+            stats->n_edges = (int64_t)run.edges.size();
+            stats->ms_screen = ms01;
+            stats->ms_ani = ms12;
+            stats->ms_total = ms01 + ms12;
+            stats->launches = c->launches - launches0;
+        }
+        return emit_edges(c, run, edges, n_edges);
+    });
+}
+
+int skb_pairs_detail(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64_t n, skb_pair_detail *out) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (n < 0 || (n && (!a || !b || !out))) return fail(c, SKB_EINVAL, "bad arguments");
+        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        if (n == 0) return SKB_OK;
+        std::vector<unsigned long long> hp((size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            if (a[i] >= (uint32_t)c->n_indexed || b[i] >= (uint32_t)c->n_indexed || a[i] == b[i])
+                return fail(c, SKB_EINVAL, "pair id out of range");
+            hp[(size_t)i] = ((unsigned long long)a[i] << 32) | b[i];
+        }
+        DevBuf<unsigned long long> d_pairs;
+        DevBuf<PairOut> d_out;
+        d_pairs.upload(hp, c->st);
+        d_out.reserve((size_t)n, 0, c->st);
+        run_ani(c, d_pairs.p, n, d_out.p);
+        std::vector<PairOut> ho((size_t)n);
+        CK(cudaMemcpyAsync(ho.data(), d_out.p, (size_t)n * sizeof(PairOut), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        for (int64_t i = 0; i < n; i++) {
+            const PairOut &o = ho[(size_t)i];
+            skb_pair_detail &d = out[i];
+            d.a = a[i];
+            d.b = b[i];
+            d.ani = o.ani;
+            d.ani_raw = o.ani_raw;
+            d.af_a = o.swapped ? o.af_r : o.af_q;
+            d.af_b = o.swapped ? o.af_q : o.af_r;
+            d.n_anchors = o.n_anchors;
+            d.n_seeds = o.n_seeds;
+            d.span_q = o.span_q;
+            d.span_r = o.span_r;
+            d.n_chains = o.n_chains;
+            d.n_chunks_used = o.n_chunks_used;
+            d.swapped = o.swapped;
+            d.overflow = o.overflow;
+        }
+        return SKB_OK;
+    });
+}
+
+int skb_shared_markers(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64_t n, int64_t *shared) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (n < 0 || (n && (!a || !b || !shared))) return fail(c, SKB_EINVAL, "bad arguments");
+        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        if (n == 0) return SKB_OK;
+        for (int64_t i = 0; i < n; i++)
+            if (a[i] >= (uint32_t)c->n_indexed || b[i] >= (uint32_t)c->n_indexed)
+                return fail(c, SKB_EINVAL, "pair id out of range");
+        DevBuf<uint32_t> da, db;
+        DevBuf<long long> dout;
+        da.upload(std::vector<uint32_t>(a, a + n), c->st);
+        db.upload(std::vector<uint32_t>(b, b + n), c->st);
+        dout.reserve((size_t)n, 0, c->st);
+        shared_markers_kernel<<<nblk((uint64_t)n * 32, 256), 256, 0, c->st>>>(c->d_markers.p, c->d_marker_off.p, da.p,
+                                                                             db.p, n, dout.p);
+        CK(cudaGetLastError());
+        c->launches++;
+        CK(cudaMemcpyAsync(shared, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return SKB_OK;
+    });
+}
+
+// ---- persistence: raw sketches (seeds + marker keys + host tables); the index is rebuilt on load
+static const char kMagic[8] = {'S', 'K', 'B', '2', '0', '0', 'v', '1'};
+
+int skb_db_save(skb_ctx *ctx, const char *dir) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!dir) return fail(c, SKB_EINVAL, "no directory");
+        const std::string path = std::string(dir) + "/sketches.skb";
+        FILE *f = fopen(path.c_str(), "wb");
+        if (!f) return fail(c, SKB_EIO, "cannot create " + path);
+        const uint64_t n = (uint64_t)c->n(), ns = c->h_seed_off.back(), nm = c->n_mkeys, nc = c->h_ctg_len.size();
+        std::vector<uint64_t> seeds(ns), mk(nm);
+        CK(cudaStreamSynchronize(c->st));
+        if (ns) CK(cudaMemcpy(seeds.data(), c->d_seeds.p, ns * 8, cudaMemcpyDeviceToHost));
+        if (nm) CK(cudaMemcpy(mk.data(), c->d_mkeys.p, nm * 8, cudaMemcpyDeviceToHost));
+        for (auto &s : seeds) s &= ~2ull;  // repeat flags are index state
+        bool ok = write_all(f, kMagic, 8) && write_all(f, &n, 8) && write_all(f, &ns, 8) && write_all(f, &nm, 8) &&
+                  write_all(f, &nc, 8) && write_all(f, c->h_seed_off.data(), (n + 1) * 8) &&
+                  write_all(f, c->h_total_len.data(), n * 8) && write_all(f, c->h_ctg_off.data(), (n + 1) * 4) &&
+                  write_all(f, c->h_ctg_len.data(), nc * 4) && write_all(f, seeds.data(), ns * 8) &&
+                  write_all(f, mk.data(), nm * 8);
+        ok = (fclose(f) == 0) && ok;
+        return ok ? SKB_OK : fail(c, SKB_EIO, "short write to " + path);
+    });
+}
+
+int skb_db_load(skb_ctx *ctx, const char *dir) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!dir) return fail(c, SKB_EINVAL, "no directory");
+        if (c->n() != 0) return fail(c, SKB_ESTATE, "context already holds genomes");
+        const std::string path = std::string(dir) + "/sketches.skb";
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) return fail(c, SKB_EIO, "cannot open " + path);
+        char magic[8];
+        uint64_t n = 0, ns = 0, nm = 0, nc = 0;
+        bool ok = read_all(f, magic, 8) && std::memcmp(magic, kMagic, 8) == 0 && read_all(f, &n, 8) &&
+                  read_all(f, &ns, 8) && read_all(f, &nm, 8) && read_all(f, &nc, 8);
+        if (!ok || n >= GID_MASK) {
+            fclose(f);
+            return fail(c, SKB_EIO, "not a sketch DB: " + path);
+        }
+        std::vector<uint64_t> seed_off(n + 1), total_len(n), seeds(ns), mk(nm);
+        std::vector<uint32_t> ctg_off(n + 1), ctg_len(nc);
+        ok = read_all(f, seed_off.data(), (n + 1) * 8) && read_all(f, total_len.data(), n * 8) &&
+             read_all(f, ctg_off.data(), (n + 1) * 4) && read_all(f, ctg_len.data(), nc * 4) &&
+             read_all(f, seeds.data(), ns * 8) && read_all(f, mk.data(), nm * 8);
+        fclose(f);
+        if (!ok || seed_off[n] != ns || ctg_off[n] != nc) return fail(c, SKB_EIO, "truncated sketch DB: " + path);
+        c->d_seeds.reserve(ns + 1, 0, c->st);
+        c->d_mkeys.reserve(nm + 1, 0, c->st);
+        if (ns) CK(cudaMemcpyAsync(c->d_seeds.p, seeds.data(), ns * 8, cudaMemcpyHostToDevice, c->st));
+        if (nm) CK(cudaMemcpyAsync(c->d_mkeys.p, mk.data(), nm * 8, cudaMemcpyHostToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->h_seed_off = seed_off;
+        c->h_total_len = total_len;
+        c->h_ctg_off = ctg_off;
+        c->h_ctg_len = ctg_len;
+        c->n_mkeys = nm;
+        c->indexed = false;
+        return SKB_OK;
+    });
+}
+
+int skb_sketch_view_get(skb_ctx *ctx, skb_sketch_view *v) {
+    if (!ctx || !v) return SKB_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    v->n_genomes = ctx->n();
+    v->n_seeds = (int64_t)ctx->h_seed_off.back();
+    v->n_marker_keys = (int64_t)ctx->n_mkeys;
+    v->n_contigs = (int64_t)ctx->h_ctg_len.size();
+    v->dev_seeds = ctx->d_seeds.p;
+    v->dev_marker_keys = ctx->d_mkeys.p;
+    v->host_seed_off = ctx->h_seed_off.data();
+    v->host_total_len = ctx->h_total_len.data();
+    v->host_ctg_off = ctx->h_ctg_off.data();
+    v->host_ctg_len = ctx->h_ctg_len.data();
+    return SKB_OK;
+}
+
+__global__ void retag_keys_kernel(const uint64_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out,
+                                  int64_t gid_delta) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = in[i];
+    out[i] = (k & ~GID_MASK) | (uint64_t)((int64_t)(k & GID_MASK) + gid_delta);
+}
+__global__ void clear_rep_kernel(const uint64_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] & ~2ull;
+}
+
+int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_seeds, int64_t n_seeds,
+                        const uint64_t *dev_marker_keys, int64_t n_marker_keys, const uint64_t *host_seed_off,
+                        const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (n_genomes < 0 || n_seeds < 0 || n_marker_keys < 0) return fail(c, SKB_EINVAL, "bad arguments");
+        if (n_genomes == 0) return SKB_OK;
+        if ((uint64_t)c->n() + (uint64_t)n_genomes >= GID_MASK) return fail(c, SKB_ELIMIT, "too many genomes");
+        const uint64_t cur = c->h_seed_off.back();
+        c->d_seeds.reserve(cur + (uint64_t)n_seeds + 1, cur, c->st);
+        c->d_mkeys.reserve(c->n_mkeys + (uint64_t)n_marker_keys + 1, c->n_mkeys, c->st);
+        if (n_seeds) {
+            clear_rep_kernel<<<nblk((uint64_t)n_seeds, 256), 256, 0, c->st>>>(dev_seeds, (uint64_t)n_seeds,
+                                                                             c->d_seeds.p + cur);
+            CK(cudaGetLastError());
+            c->launches++;
+        }
+        // the sender tagged its keys with ids first_src .. ; the first imported genome becomes c->n()
+        if (n_marker_keys) {
+            // senders export a whole context, whose ids start at 0: shift them behind this context's genomes
+            retag_keys_kernel<<<nblk((uint64_t)n_marker_keys, 256), 256, 0, c->st>>>(
+                dev_marker_keys, (uint64_t)n_marker_keys, c->d_mkeys.p + c->n_mkeys, (int64_t)c->n());
+            CK(cudaGetLastError());
+            c->launches++;
+        }
+        CK(cudaStreamSynchronize(c->st));
+        const uint32_t ctg_base = (uint32_t)c->h_ctg_len.size();
+        for (int32_t g = 0; g < n_genomes; g++) {
+            c->h_seed_off.push_back(cur + (host_seed_off[g + 1] - host_seed_off[0]));
+            c->h_total_len.push_back(host_total_len[g]);
+            for (uint32_t k = host_ctg_off[g]; k < host_ctg_off[g + 1]; k++) c->h_ctg_len.push_back(host_ctg_len[k]);
+            c->h_ctg_off.push_back(ctg_base + (host_ctg_off[g + 1] - host_ctg_off[0]));
+        }
+        c->n_mkeys += (uint64_t)n_marker_keys;
+        c->indexed = false;
+        return SKB_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared definitions for the sm_100a ANI/AF kernels: record layouts, device views, small helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/skani_b200.h"
+
+namespace skb {
+
+// ---- fixed algorithm constants (skani defaults) ----------------------
+constexpr int K_SEED = 15;
+constexpr int K_MARKER = 21;
+constexpr uint64_t C_SEED = 125;
+constexpr uint64_t C_MARKER = 1000;
+constexpr uint64_t THR_SEED = 0xFFFFFFFFFFFFFFFFull / C_SEED;
+constexpr uint64_t THR_MARKER = 0xFFFFFFFFFFFFFFFFull / C_MARKER;
+constexpr uint64_t MASK_MARKER = (~0ull) >> (64 - 2 * K_MARKER);
+constexpr uint64_t MASK_SEED = (~0ull) >> (64 - 2 * K_SEED);
+constexpr uint32_t CONTIG_PAD = 4096;  // virtual gap between contigs in genome coordinates
+constexpr int LOOKBACK = 32;           // chaining look-back in anchors == warp width
+
+// ---- packed seed record: kmer(30) << 34 | padded_pos(32) << 2 | rep << 1 | strand -------------
+__host__ __device__ inline uint32_t seed_kmer(uint64_t s) { return (uint32_t)(s >> 34); }
+__host__ __device__ inline uint32_t seed_pos(uint64_t s) { return (uint32_t)((s >> 2) & 0xffffffffu); }
+__host__ __device__ inline int seed_rep(uint64_t s) { return (int)((s >> 1) & 1); }
+__host__ __device__ inline int seed_strand(uint64_t s) { return (int)(s & 1); }
+
+// ---- marker key of the inverted index: marker(42) << 22 | genome id(22) -----------------------
+constexpr int GID_BITS = 22;
+constexpr uint64_t GID_MASK = (1ull << GID_BITS) - 1;
+
+constexpr uint64_t TAB_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+// minimap2/skani invertible 64-bit mix; first line is ~(key + (key << 21)) (see oracle)
+__host__ __device__ inline uint64_t mm_hash64(uint64_t key) {
+    key = ~(key + (key << 21));
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+__host__ __device__ inline uint32_t tab_slot(uint32_t kmer, int bits) {
+    return (uint32_t)(kmer * 0x9E3779B1u) >> (32 - bits);
+}
+
+// Device view of the sketch DB (all pointers device memory)
+struct DbView {
+    int32_t n_genomes;
+    const uint64_t *seeds;       // position-ordered records, all genomes
+    const uint64_t *g_seed_off;  // [n+1]
+    const uint64_t *tab;         // open-addressing seed index, all genomes
+    const uint64_t *g_tab_off;   // [n+1]
+    const uint8_t *g_tab_bits;   // [n] log2(slots)
+    const uint32_t *chunk_begin; // genome g: n_chunks(g)+1 entries at g_chunk_off[g] + g (seed index relative to genome)
+    const uint32_t *chunk_start; // [total chunks] padded coordinate of first base
+    const uint32_t *chunk_len;   // [total chunks]
+    const uint32_t *g_chunk_off; // [n+1]
+    const uint32_t *ctg_pstart;  // [total contigs] padded coordinate of contig base 0
+    const uint32_t *ctg_len;     // [total contigs]
+    const uint32_t *g_ctg_off;   // [n+1]
+    const uint64_t *g_total_len; // [n]
+    const uint64_t *markers;     // per-genome sorted unique markers
+    const uint64_t *g_marker_off;// [n+1]
+    const uint64_t *inv_keys;    // sorted unique (marker << 22 | gid)
+    int64_t n_inv;
+};
+
+struct PairOut {
+    double ani, ani_raw, af_q, af_r;
+    int64_t n_anchors, n_seeds, span_q, span_r;
+    int32_t n_chains, n_chunks_used, swapped, overflow;
+};
+
+}  // namespace skb

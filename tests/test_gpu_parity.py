@@ -1,0 +1,160 @@
+"""GPU parity: every stage of the CUDA path against the CPU oracle on identical inputs (through the C-ABI)."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng7(built_lib, genomes7):
+    from skder_b200 import engine
+
+    e = engine.Engine(0)
+    packed = e.add_fasta(genomes7, threads=4)
+    e.index()
+    yield e, packed
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def ora7(oracle, genomes7):
+    return [oracle.Sketch.from_file(f) for f in genomes7]
+
+
+def test_pack_matches_oracle_ingest(eng7, ora7):
+    _, packed = eng7
+    for p, s in zip(packed, ora7):
+        assert p.n_bases == s.total_len
+        assert p.n_contigs == s.n_contigs
+        assert np.array_equal(p.contig_lens(), s.contig_lens())
+        assert p.first_name == s.first_name
+
+
+def test_seeds_bit_exact(eng7, ora7):
+    e, _ = eng7
+    for g, s in enumerate(ora7):
+        mine, ref = e.seeds(g), s.seeds()
+        assert len(mine) == len(ref), (g, len(mine), len(ref))
+        assert np.array_equal(mine, ref), "genome %d: first diff at %d" % (g, int(np.argmax(mine != ref)))
+
+
+def test_markers_bit_exact(eng7, ora7):
+    e, _ = eng7
+    for g, s in enumerate(ora7):
+        assert np.array_equal(e.markers(g), s.markers())
+        assert e.sizes(g)["n_chunks"] == s.n_chunks
+
+
+def test_shared_marker_counts_bit_exact(eng7, ora7, oracle):
+    e, _ = eng7
+    pairs = list(itertools.combinations(range(7), 2))
+    a = [p[0] for p in pairs]
+    b = [p[1] for p in pairs]
+    got = e.shared_markers(a, b)
+    want = [oracle.screen(ora7[i], ora7[j], 0.8)[0] for i, j in pairs]
+    assert list(got) == want
+
+
+def test_pairs_integer_exact_and_float_close(eng7, ora7, oracle):
+    e, _ = eng7
+    pairs = list(itertools.combinations(range(7), 2)) + [(3, 1), (6, 0)]
+    det = e.pairs_detail([p[0] for p in pairs], [p[1] for p in pairs])
+    for (i, j), d in zip(pairs, det):
+        r = oracle.pair(ora7[i], ora7[j])
+        assert (d.swapped, d.n_chains, d.n_anchors, d.n_seeds, d.span_q, d.span_r, d.n_chunks_used) == (
+            r.swapped, r.n_chains, r.n_anchors_total, r.n_seeds_total, r.span_q, r.span_r, r.n_chunks_used), (i, j)
+        assert d.overflow == 0
+        # tolerance: same IEEE expressions; device pow() vs glibc pow() may differ in the last ulps
+        assert abs(d.ani_raw - r.ani_raw) < 1e-12 and abs(d.ani - r.ani) < 1e-12
+        assert abs(d.af_a - r.af_a) < 1e-15 and abs(d.af_b - r.af_b) < 1e-15
+
+
+def test_triangle_screen_and_edges(eng7, ora7, oracle):
+    e, _ = eng7
+    edges, st = e.triangle(screen=89.0, min_af=50.0)
+    want = {}
+    for i, j in itertools.combinations(range(7), 2):
+        if not oracle.screen(ora7[i], ora7[j], 0.89)[1]:
+            continue
+        r = oracle.pair(ora7[i], ora7[j])
+        if r.ani >= 0 and max(r.af_a, r.af_b) * 100 >= 50.0:
+            want[(i, j)] = ("%.2f" % (r.ani * 100), "%.2f" % (r.af_a * 100), "%.2f" % (r.af_b * 100))
+    got = {(int(x["a"]), int(x["b"])): ("%.2f" % x["ani"], "%.2f" % x["af_a"], "%.2f" % x["af_b"]) for x in edges}
+    assert got == want
+    assert st.n_pairs_total == 21 and st.n_edges == len(want)
+    # a screen nobody passes -> no pairs, no edges
+    edges2, st2 = e.triangle(screen=99.999, min_af=0.0)
+    none_pass = not any(oracle.screen(ora7[i], ora7[j], 0.99999)[1] for i, j in itertools.combinations(range(7), 2))
+    if none_pass:
+        assert len(edges2) == 0 and st2.n_pairs_screened == 0
+
+
+def test_triangle_partitions_cover_triangle(eng7):
+    e, _ = eng7
+    full, _ = e.triangle(screen=80.0, min_af=0.0)
+    parts = [e.triangle(screen=80.0, min_af=0.0, part=p, n_parts=3)[0] for p in range(3)]
+    cat = np.sort(np.concatenate(parts), order=["a", "b"])
+    assert np.array_equal(cat, np.sort(full, order=["a", "b"]))
+
+
+def test_rect_equals_triangle_values(eng7):
+    e, _ = eng7
+    tri, _ = e.triangle(screen=80.0, min_af=0.0)
+    tv = {(int(x["a"]), int(x["b"])): (x["ani"], x["af_a"], x["af_b"]) for x in tri}
+    refs, queries = [0, 2, 5, 6], [1, 3, 4]
+    rect, st = e.rect(refs, queries, screen=80.0, min_af=0.0)
+    assert st.n_pairs_total == 12
+    for x in rect:
+        a, b = int(x["a"]), int(x["b"])
+        assert a in refs and b in queries
+        if a < b:
+            assert tv[(a, b)] == (x["ani"], x["af_a"], x["af_b"])
+        else:  # same estimator, roles swapped back
+            assert tv[(b, a)] == (x["ani"], x["af_b"], x["af_a"])
+    assert len(rect) == 12
+
+
+def test_db_roundtrip(eng7, tmp_path):
+    from skder_b200 import engine
+
+    e, _ = eng7
+    e.save(str(tmp_path))
+    with engine.Engine(0) as e2:
+        e2.load(str(tmp_path))
+        e2.index()
+        assert e2.n_genomes == 7
+        for g in range(7):
+            assert np.array_equal(e.seeds(g), e2.seeds(g))
+            assert np.array_equal(e.markers(g), e2.markers(g))
+        t1, _ = e.triangle(80.0, 0.0)
+        t2, _ = e2.triangle(80.0, 0.0)
+        assert np.array_equal(t1, t2)
+
+
+def test_synthetic_clades(oracle, built_lib):
+    from skder_b200 import engine, synth
+
+    gens = [c for _, _, c in synth.config_genomes("tiny")]
+    sk = [oracle.Sketch.from_contigs(c) for c in gens]
+    with engine.Engine(0) as e:
+        e.add([engine.pack_contigs(c) for c in gens])
+        e.index()
+        for g, s in enumerate(sk):
+            assert np.array_equal(e.seeds(g), s.seeds())
+            assert np.array_equal(e.markers(g), s.markers())
+        edges, st = e.triangle(screen=80.0, min_af=15.0)
+        n = len(gens)
+        want = {}
+        for i, j in itertools.combinations(range(n), 2):
+            if not oracle.screen(sk[i], sk[j], 0.80)[1]:
+                continue
+            r = oracle.pair(sk[i], sk[j])
+            if r.ani >= 0 and max(r.af_a, r.af_b) * 100 >= 15.0:
+                want[(i, j)] = ("%.2f" % (r.ani * 100), "%.2f" % (r.af_a * 100), "%.2f" % (r.af_b * 100))
+        got = {(int(x["a"]), int(x["b"])): ("%.2f" % x["ani"], "%.2f" % x["af_a"], "%.2f" % x["af_b"]) for x in edges}
+        assert got == want
+        # 3 clades x 4: only within-clade pairs survive
+        assert len(want) == 3 * 6
