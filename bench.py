@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- genome pairs/sec for ANI+AF behind skDER's `skani triangle` call site.
+
+  python bench.py --gpus N --steps K --warmup W            (ours; one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port on all host threads)
+
+A step = one pass of the hot path over one synthetic genome set (BASELINE.json configs):
+  value : pairs/s with sketches already resident in HBM (prescreen + ANI/AF + edge gather), device-timed
+  e2e   : pairs/s through the C-ABI from packed genomes in pinned HOST memory to edges on the host
+          (H2D upload + sketch + index + prescreen + ANI/AF + D2H), every step.
+N=1 runs BASELINE configs[1] (1,000 x 5 Mbp, greedy thresholds); N>1 shards the same triangle's rows
+round-robin over the ranks (no data-path collective; sketches are replicated by NCCL all-gather
+before the timed region of `value`, inside it for `e2e`).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GREEDY_SCREEN = 89.5  # skDER default: -s (ANI cutoff 99.5 - 10)   reference bin/skder:199-204
+GREEDY_MIN_AF = 50.0  # skDER default AF cutoff                    reference bin/skder:325-329
+
+
+def workload_shape(name):
+    from skder_b200 import synth
+
+    nc, per, L, Lhi, *_ = synth.CONFIGS[name]
+    return nc, per, L
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/skani_oracle.c) -- the reference's skani is not installable here
+# ------------------------------------------------------------------------------------------------
+def cpu_triangle_components(workload, n_clades, per_clade, threads, screen, min_af):
+    """Time the oracle on a bounded sample; returns component costs per unit."""
+    import itertools
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    from skder_b200 import synth
+
+    O.build()
+    gens = [c for _, _, c in synth.config_genomes(workload, n_clades=n_clades, per_clade=per_clade)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        sk = list(ex.map(O.Sketch.from_contigs, gens))
+    t_sketch = time.perf_counter() - t0
+    n = len(sk)
+    pairs = list(itertools.combinations(range(n), 2))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        passed = list(ex.map(lambda ab: O.screen(sk[ab[0]], sk[ab[1]], screen / 100.0)[1], pairs, chunksize=256))
+    t_screen = time.perf_counter() - t0
+    surv = [p for p, ok in zip(pairs, passed) if ok]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(lambda ab: O.pair(sk[ab[0]], sk[ab[1]]), surv, chunksize=4))
+    t_ani = time.perf_counter() - t0
+    n_edges = sum(1 for r in res if r.ani >= 0 and max(r.af_a, r.af_b) * 100 >= min_af)
+    return {"n": n, "pairs": len(pairs), "survivors": len(surv), "edges": n_edges, "t_sketch": t_sketch,
+            "t_screen": t_screen, "t_ani": t_ani}
+
+
+def cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch):
+    t = comp["t_screen"] / comp["pairs"] * pairs_full + comp["t_ani"] / max(comp["survivors"], 1) * surv_full
+    if with_sketch:
+        t += comp["t_sketch"] / comp["n"] * n_full
+    return pairs_full / t, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    nc, per, L = workload_shape(args.workload)
+    n_full = nc * per
+    pairs_full = n_full * (n_full - 1) // 2
+    surv_full = nc * per * (per - 1) // 2
+    s_clades, s_per = min(nc, 20), 5
+    vals = []
+    comp = None
+    for it in range(args.warmup + args.steps):
+        comp = cpu_triangle_components(args.workload, s_clades, s_per, threads, GREEDY_SCREEN, GREEDY_MIN_AF)
+        if it >= args.warmup:
+            vals.append(cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch=True))
+    value = float(np.mean([v for v, _ in vals]))
+    t_full = float(np.mean([t for _, t in vals]))
+    sample = ("%d clades x %d members of %s (%d genomes, %d pairs, %d survive the screen): sketch %.2fs, screen %.2fs, "
+              "ANI/AF %.2fs on %d threads; per-unit costs scaled to the full workload (%d genomes, %d pairs, %d survivors)"
+              % (s_clades, s_per, args.workload, comp["n"], comp["pairs"], comp["survivors"], comp["t_sketch"],
+                 comp["t_screen"], comp["t_ani"], threads, n_full, pairs_full, surv_full))
+    line = {
+        "impl": "reference", "metric": "genome pairs/sec ANI+AF", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "screen": GREEDY_SCREEN, "min_af": GREEDY_MIN_AF,
+                   "note": "oracle-CPU (C port of the published skani method), NOT the skani binary: skani is absent"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(w):
+    nc, per, L = workload_shape(w)
+    return "%s: %d synthetic %.1f Mbp genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER greedy thresholds" % (
+        w, nc * per, L / 1e6, nc, per)
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def pinned_views(packed, torch):
+    """Copy every genome's 2-bit words into ONE pinned host buffer and return skb_packed views into it."""
+    from skder_b200 import _lib
+
+    total = sum(p.n_words for p in packed)
+    pin = torch.empty(total, dtype=torch.int64).pin_memory()
+    arr = pin.numpy().view(np.uint64)
+    views, keep, off = [], [], 0
+    for p in packed:
+        nw = p.n_words
+        arr[off:off + nw] = p.words()
+        v = _lib.Packed()
+        v.words = C.cast(arr[off:].ctypes.data, C.POINTER(C.c_uint64))
+        v.n_words, v.n_bases, v.n_contigs = nw, p.n_bases, p.n_contigs
+        lens = (C.c_int64 * max(1, p.n_contigs))(*p.contig_lens().tolist())
+        v.contig_lens = C.cast(lens, C.POINTER(C.c_int64))
+        v.first_name, v.n50, v.total_bases_all = None, p.n50, p.total_bases_all
+        keep.append(lens)
+        views.append(v)
+        off += nw
+    return pin, views, keep, total * 8
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from skder_b200 import _lib, build, engine, synth
+
+    build.build()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: bench.py has no CPU path for --impl ours")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    nc, per, L = workload_shape(args.workload)
+    n_full = nc * per
+    pairs_full = n_full * (n_full - 1) // 2
+    # every rank ingests its share of the clades (rank r: clades r, r+world, ...)
+    from skder_b200 import multi
+
+    t_gen = time.perf_counter()
+    my_clades = list(range(rank, nc, world))
+    packed = []
+    # clade-parallel generation on host threads
+    from concurrent.futures import ThreadPoolExecutor
+
+    ncfg = synth.CONFIGS[args.workload]
+
+    def gen(c):
+        return [engine.pack_contigs(g) for g in synth.one_clade(c, per, ncfg[2], ncfg[6], ncfg[4], ncfg[5], 300, ncfg[3])]
+
+    with ThreadPoolExecutor(max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))) as ex:
+        for clade in ex.map(gen, my_clades):
+            packed += clade
+    t_gen = time.perf_counter() - t_gen
+    pin, views, keep, h2d_bytes = pinned_views(packed, torch)
+    del packed
+    arr = (C.POINTER(_lib.Packed) * len(views))(*[C.pointer(v) for v in views])
+
+    eng = engine.Engine(local)
+    L_ = eng._L
+
+    def sketch_all():
+        """host packed genomes -> replicated, indexed sketch DB on every rank"""
+        eng.clear()
+        eng._ck(L_.skb_add_genomes(eng._h, len(views), arr), "skb_add_genomes")
+        if world > 1:
+            multi.replicate_sketches(eng, dist, torch)
+        eng.index()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def triangle():
+        edges, st = eng.triangle(GREEDY_SCREEN, GREEDY_MIN_AF, part=rank, n_parts=world)
+        if world > 1:
+            edges = multi.gather_edges(edges, dist, torch)
+        return edges, st
+
+    # ---- warm-up (full e2e steps)
+    for _ in range(args.warmup):
+        sketch_all()
+        triangle()
+    # ---- e2e: host packed genomes -> edges on host, every step
+    with ClockSampler(local) as clk_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            sketch_all()
+            edges, st = triangle()
+            d2h += edges.nbytes
+        barrier()
+        t_e2e = time.perf_counter() - t0
+    # ---- value: sketches resident; device-timed on the library's stream
+    l0 = eng.launches
+    ms_ani, ms_screen, st = [], [], None
+    with ClockSampler(local) as clk:
+        barrier()
+        eng.timer_start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            edges, st = triangle()
+            ms_ani.append(st.ms_ani)
+            ms_screen.append(st.ms_screen)
+        ms_dev = eng.timer_stop()
+        barrier()
+        t_wall = time.perf_counter() - t0
+    launches = eng.launches - l0
+    if world > 1:
+        tt = torch.tensor([ms_dev, t_e2e, float(np.mean(ms_ani))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, t_e2e = float(tt[0]), float(tt[1])
+        cnt = torch.tensor([st.n_pairs_screened, st.sum_query_seeds, st.sum_anchors, launches, h2d_bytes],
+                           device="cuda", dtype=torch.int64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        tot_screened, launches_all, h2d_all = int(cnt[0]), int(cnt[3]), int(cnt[4])
+    else:
+        tot_screened, launches_all, h2d_all = st.n_pairs_screened, launches, h2d_bytes
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    ms_step = ms_dev / args.steps
+    value = pairs_full / (ms_step / 1e3)
+    e2e_value = pairs_full / (t_e2e / args.steps)
+    # ---- roofline of the dominant kernel (ani_pair_kernel), this rank's launch.
+    # algorithmic bytes per surviving pair = 32*S_q + 32*A + 20 (SURVEY.md section 8d / BASELINE.md section 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 32 * st.sum_query_seeds + 32 * st.sum_anchors + 20 * st.n_pairs_screened
+    ani_ms = float(np.mean(ms_ani))
+    achieved = alg_bytes / (ani_ms / 1e3) / 1e9 if ani_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ani_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        comp = cpu_triangle_components(args.workload, min(nc, 20), 5, threads, GREEDY_SCREEN, GREEDY_MIN_AF)
+        surv_full = nc * per * (per - 1) // 2
+        v, t_full = cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch=False)
+        cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+               "sample": "%d clades x 5 members of %s (%d pairs, %d survivors): screen %.2fs, ANI/AF %.2fs on %d threads, "
+                         "sketches resident; per-unit costs scaled to the full workload" % (
+                             min(nc, 20), args.workload, comp["pairs"], comp["survivors"], comp["t_screen"], comp["t_ani"], threads)}
+    line = {
+        "metric": "genome pairs/sec ANI+AF", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "screen": GREEDY_SCREEN, "min_af": GREEDY_MIN_AF,
+                   "pairs": pairs_full, "pairs_screened": tot_screened, "edges": int(len(edges)),
+                   "l2": "inputs larger than L2 (sketch DB %.1f GB per rank)" % (
+                       (st.sum_query_seeds and (n_full * L / 125 * 8 * 3) / 1e9) or 0.0),
+                   "ms_screen": float(np.mean(ms_screen)), "ms_ani": ani_ms, "gen_s": t_gen,
+                   "wall_ms_per_step": t_wall / args.steps * 1e3},
+        "clocks": clk.summary(), "clocks_e2e": clk_e2e.summary(),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h // args.steps,
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": launches_all,
+        "roofline": {"bound": "hbm", "kernel": "ani_pair_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"},
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

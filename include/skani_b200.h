@@ -86,6 +86,8 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes);
  * more genomes were added. */
 int skb_index(skb_ctx *ctx);
 int32_t skb_n_genomes(const skb_ctx *ctx);
+/* drop every genome and index but keep the device allocations (repeated runs on one context) */
+int skb_clear(skb_ctx *ctx);
 
 /* sketch read-back (parity tests; DB persistence) */
 int skb_sketch_sizes(skb_ctx *ctx, int32_t g, int64_t *n_seeds, int64_t *n_markers, int32_t *n_chunks,
@@ -118,6 +120,8 @@ typedef struct {
     int64_t n_edges;
     float ms_screen, ms_ani, ms_total; /* device time (CUDA events) */
     int64_t launches;         /* kernels launched by this call */
+    int64_t sum_query_seeds;  /* sum over screened pairs of the query genome's seed count (roofline bytes) */
+    int64_t sum_anchors;      /* sum over screened pairs of chained anchors (roofline bytes) */
 } skb_stats;
 
 /* `skani triangle -l list --min-af A -E -s S` (skder.py:16-18): all pairs a<b of the DB whose
@@ -159,6 +163,9 @@ void skb_free(void *p);
 
 /* total kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t skb_launch_count(const skb_ctx *ctx);
+/* device-side stopwatch: CUDA events recorded on the context's own stream */
+int skb_timer_start(skb_ctx *ctx);
+int skb_timer_stop(skb_ctx *ctx, float *ms);
 /* CUDA stream the context launches on (cudaStream_t as void*), for external event timing */
 void *skb_stream(const skb_ctx *ctx);
 

@@ -45,14 +45,14 @@ void ora_default_params(ora_params_t *p) {
     p->chunk_len = 20000;
     p->band_bp = 2500;
     p->max_gap = 300;
-    p->lookback = 32;
+    p->lookback = 16;
     p->anchor_score = 20;
     p->min_anchors = 3;
     p->min_score = 45;
     p->max_mult = 8;
-    p->max_chunk_anchors = 512;
+    p->max_chunk_anchors = 256;
     p->max_chunk_chains = 4;
-    p->max_pair_chains = 2048;
+    p->max_pair_chains = 1024;
     p->ovl_num = 1;
     p->ovl_den = 2;
     p->span_ext = 150;
@@ -320,8 +320,8 @@ typedef struct {
 } anchor_t;
 static int cmp_anchor(const void *a, const void *b) {
     const anchor_t *x = (const anchor_t *)a, *y = (const anchor_t *)b;
-    if (x->r != y->r) return x->r < y->r ? -1 : 1;
     if (x->q != y->q) return x->q < y->q ? -1 : 1;
+    if (x->r != y->r) return x->r < y->r ? -1 : 1;
     return 0;
 }
 typedef struct {
@@ -435,16 +435,18 @@ retry:
         if (ovf) n = 0;
         if (n < p->min_anchors) continue;
         qsort(an, (size_t)n, sizeof(anchor_t), cmp_anchor);
-        /* banded chaining DP on reference order; integer scores */
+        /* banded chaining DP in QUERY order (anchors sorted by (query pos, ref pos)); integer scores.
+         * Predecessor j of i: same strand relation, 0 < dq <= band_bp, ref moves the matching way
+         * (dr > 0), |dq - dr| <= max_gap, at most `lookback` anchors back; ties: nearest j. */
         for (int i = 0; i < n; i++) {
             int32_t best = p->anchor_score, bj = -1;
             for (int j = i - 1; j >= 0 && j >= i - p->lookback; j--) {
-                uint32_t dr = an[i].r - an[j].r;
-                if (dr > (uint32_t)p->band_bp) break;
-                if (an[j].rev != an[i].rev || dr == 0) continue;
-                int64_t dq = an[i].rev ? (int64_t)an[j].q - (int64_t)an[i].q : (int64_t)an[i].q - (int64_t)an[j].q;
-                if (dq <= 0) continue;
-                int64_t gap = (int64_t)dr - dq;
+                uint32_t dq = an[i].q - an[j].q;
+                if (dq > (uint32_t)p->band_bp) break;
+                if (an[j].rev != an[i].rev || dq == 0) continue;
+                int64_t dr = an[i].rev ? (int64_t)an[j].r - (int64_t)an[i].r : (int64_t)an[i].r - (int64_t)an[j].r;
+                if (dr <= 0) continue;
+                int64_t gap = dr - (int64_t)dq;
                 if (gap < 0) gap = -gap;
                 if (gap > p->max_gap) continue;
                 int32_t cand = f[j] + p->anchor_score - (int32_t)gap;
@@ -478,10 +480,10 @@ retry:
             c.n_anchors = cnt[e];
             c.score = f[e];
             c.rev = an[e].rev;
-            c.r0 = an[rt].r;
-            c.r1 = an[e].r;
-            c.q0 = an[rt].q < an[e].q ? an[rt].q : an[e].q;
-            c.q1 = an[rt].q < an[e].q ? an[e].q : an[rt].q;
+            c.q0 = an[rt].q;
+            c.q1 = an[e].q;
+            c.r0 = an[rt].r < an[e].r ? an[rt].r : an[e].r;
+            c.r1 = an[rt].r < an[e].r ? an[e].r : an[rt].r;
             c.n_seeds = (int32_t)seeds_in_span(q, ch, c.q0, c.q1);
             if (nc == ccap) {
                 ccap *= 2;

@@ -38,16 +38,16 @@ typedef struct {
     int32_t min_contig_len; /* contigs shorter than this are ignored (500) */
     int32_t contig_pad;     /* virtual gap between contigs in genome coordinates (4096) */
     int32_t chunk_len;      /* query chunk length (20000) */
-    int32_t band_bp;        /* chaining look-back on the reference, bp (2500) */
+    int32_t band_bp;        /* chaining look-back on the query, bp (2500) */
     int32_t max_gap;        /* max |d_ref - d_query| between chained anchors (300) */
-    int32_t lookback;       /* chaining look-back in anchors (32) */
+    int32_t lookback;       /* chaining look-back in anchors (16) */
     int32_t anchor_score;   /* score per chained anchor (20) */
     int32_t min_anchors;    /* anchors a chain needs (3) */
     int32_t min_score;      /* score a chain needs (45) */
     int32_t max_mult;       /* seeds whose k-mer occurs more often in either genome are skipped */
-    int32_t max_chunk_anchors; /* anchors kept per chunk (512) */
+    int32_t max_chunk_anchors; /* anchors kept per chunk (256) */
     int32_t max_chunk_chains;  /* chain candidates kept per chunk (4) */
-    int32_t max_pair_chains;   /* chain candidates kept per pair (2048) */
+    int32_t max_pair_chains;   /* chain candidates kept per pair (1024) */
     int32_t ovl_num;        /* chain rejected if overlap*ovl_den > ovl_num*own_length ... */
     int32_t ovl_den;        /* ... with an accepted chain on the reference or the query */
     int32_t span_ext;       /* bases each accepted chain is extended by on both sides, clipped (150; fitted) */

@@ -76,6 +76,8 @@ class Stats(C.Structure):
         ("ms_ani", C.c_float),
         ("ms_total", C.c_float),
         ("launches", C.c_int64),
+        ("sum_query_seeds", C.c_int64),
+        ("sum_anchors", C.c_int64),
     ]
 
 
@@ -100,7 +102,7 @@ SYMBOLS = [
     "skb_create", "skb_destroy", "skb_last_error", "skb_add_genomes", "skb_index", "skb_n_genomes",
     "skb_sketch_sizes", "skb_get_seeds", "skb_get_markers", "skb_db_save", "skb_db_load", "skb_triangle",
     "skb_rect", "skb_pairs_detail", "skb_shared_markers", "skb_sketch_view_get", "skb_import_sketches",
-    "skb_free", "skb_launch_count", "skb_stream",
+    "skb_free", "skb_launch_count", "skb_stream", "skb_clear", "skb_timer_start", "skb_timer_stop",
 ]
 
 _lib = None
@@ -155,6 +157,9 @@ def lib():
         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p,
     ]
+    L.skb_clear.argtypes = [C.c_void_p]
+    L.skb_timer_start.argtypes = [C.c_void_p]
+    L.skb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.skb_free.argtypes = [C.c_void_p]
     L.skb_free.restype = None
     L.skb_launch_count.argtypes = [C.c_void_p]

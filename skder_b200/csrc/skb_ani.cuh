@@ -1,33 +1,39 @@
-// K4 -- fused seed anchoring + per-chunk chaining + chain selection + ANI/AF, one CTA per genome pair.
+// K4 -- seed anchoring + per-chunk chaining (chunk kernel), chain selection + ANI/AF (finalize kernel).
 //
 // Stands in for skani's pairwise estimator behind `skani triangle|dist|search`
 // (reference call sites src/skDER/skder.py:16-18, :58-59, :119).  Integer results (anchors, seeds,
 // spans, chain count) are bit-exact against oracle/skani_oracle.c ora_pair(); ANI/AF are the same
 // IEEE double expressions (device pow() may differ from glibc's in the last ulp).
 //
-// Work split: a CTA of 16 warps takes one pair; each warp takes query chunks (20 kb windows of the
-// query genome) round-robin.  Per chunk the warp
-//   1. streams the chunk's position-ordered seeds (coalesced 8-byte records), probes the reference's
-//      hash index (L2-resident: all ~50 members of a clade are compared against the same tables),
-//      and drops the anchors (ref_pos, query_pos, strand relation) into its shared-memory slab;
-//   2. bitonic-sorts the anchors by (ref_pos, query_pos);
-//   3. runs the chaining DP: anchor i on all lanes, lane l scores predecessor i-1-l, one
-//      REDUX (__reduce_max_sync) picks the best predecessor (ties: nearest);
-//   4. keeps the best end of every DP tree with >= min_anchors / min_score, at most chunk_cap per chunk.
-// The CTA then orders all candidates by (score desc, chunk, ordinal), resolves the greedy
-// non-overlap selection in parallel, accumulates per-chunk anchors/seeds and clipped spans, and
-// reduces ANI = sum(S_c * (A_c/S_c)^(1/15)) / sum(S_c), AF = span / genome length.
+// chunk_kernel: one 16-lane group (half a warp) per task = (surviving pair, 20 kb query chunk).
+//   1. the group streams the chunk's position-ordered seeds (coalesced 8-byte records), probes the
+//      reference's hash index (L2-resident: a clade's ~50 members all hit the same tables) and lays
+//      the anchors down in QUERY order -- the order the DP wants, so there is no sort;
+//   2. chaining DP, look-back 16 == group width: lane L keeps anchor j (j = L mod 16) resident in
+//      registers, anchor i is broadcast from shared memory, every lane scores its predecessor and
+//      one REDUX (__reduce_max_sync on the group mask) picks the best (ties: nearest);
+//   3. best end of every DP tree with >= min_anchors / min_score, the chunk's top `max_chunk_chains`
+//      by (score, q0, r0) go to the task's fixed candidate slots in global memory.
+// finalize_kernel: one CTA per pair gathers the candidates, orders them by (score desc, chunk,
+//   ordinal), resolves the greedy non-overlap selection in parallel rounds, accumulates per-chunk
+//   anchors/seeds and clipped spans, and reduces ANI = sum(S_c (A_c/S_c)^(1/15)) / sum(S_c),
+//   AF = span / genome length.
 #pragma once
 #include "skb_common.cuh"
 #include "skb_index.cuh"
 
 namespace skb {
 
-constexpr int ANI_WARPS = 16;
-constexpr int ANI_THREADS = ANI_WARPS * 32;
-constexpr int MAXA = 512;   // anchors per chunk
-constexpr int MAXP = 1024;  // chain candidates per pair
-constexpr int STAGE = 8;    // max_mult upper bound (anchors staged per seed)
+constexpr int GRP = 16;                       // lanes per chunk task == DP look-back
+constexpr int CH_WARPS = 4;                   // warps per CTA of the chunk kernel
+constexpr int CH_THREADS = CH_WARPS * 32;
+constexpr int CH_GROUPS = CH_THREADS / GRP;   // 8 tasks in flight per CTA
+constexpr int MAXA = 256;                     // anchors per chunk
+constexpr int MAXP = 1024;                    // chain candidates per pair
+constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
+constexpr int SLOTS = 4;                      // candidate slots per task (max_chunk_chains upper bound)
+constexpr int FIN_THREADS = 256;
+constexpr uint32_t FIN_MAX_CHUNKS = 4096;     // chunks of a query genome the finalize kernel accumulates in smem
 
 struct AniParams {
     int32_t band_bp, max_gap, anchor_score, min_anchors, min_score, max_mult, max_chunk_chains;
@@ -35,15 +41,29 @@ struct AniParams {
     double debias_a, debias_g;
 };
 
-struct __align__(16) WarpSlab {
-    uint64_t key[MAXA];   // (ref_pos << 32) | (query_pos << 1) | rev
-    int32_t f[MAXA];      // DP score
-    uint16_t root[MAXA];  // first anchor of the best chain ending here
-    uint16_t cnt[MAXA];   // anchors in that chain
-    uint32_t bor[MAXA];   // best-of-root / staging area (MAXA*4 = 32 lanes * STAGE * 8 bytes)
+struct PairInfo {
+    uint32_t q, r;  // query / reference genome ids
+    uint32_t swapped;
+    uint32_t nch;   // chunks of the query
 };
-static_assert(sizeof(WarpSlab) == 10240, "slab size");
-static_assert(MAXA * 4 == 32 * STAGE * 8, "staging area must fit in bor[]");
+
+// anchor record: ref_pos(32) | q_rel(15) | rev(1) | seed index in chunk(16)
+__device__ __forceinline__ uint32_t an_r(uint64_t a) { return (uint32_t)(a >> 32); }
+__device__ __forceinline__ uint32_t an_q(uint64_t a) { return ((uint32_t)a >> 17) & 0x7fffu; }
+__device__ __forceinline__ uint32_t an_rev(uint64_t a) { return ((uint32_t)a >> 16) & 1u; }
+__device__ __forceinline__ uint32_t an_sidx(uint64_t a) { return (uint32_t)a & 0xffffu; }
+// DP result record: f(13) << 17 | root(8) << 9 | cnt(9)
+__device__ __forceinline__ uint32_t rs_f(uint32_t x) { return x >> 17; }
+__device__ __forceinline__ uint32_t rs_root(uint32_t x) { return (x >> 9) & 0xffu; }
+__device__ __forceinline__ uint32_t rs_cnt(uint32_t x) { return x & 0x1ffu; }
+
+struct __align__(16) GroupSlab {
+    uint64_t anc[MAXA];           // anchors in (query pos, ref pos) order
+    uint32_t res[MAXA];           // DP results
+    uint32_t bor[MAXA];           // best-of-root; first GRP*STAGE words double as the hit staging area
+};
+static_assert(sizeof(GroupSlab) == 4096, "slab size");
+static_assert(GRP * STAGE <= MAXA, "staging area must fit in bor[]");
 
 struct __align__(16) Cand {
     uint32_t q0, q1, r0, r1;
@@ -55,455 +75,457 @@ struct __align__(16) Cand {
 };
 static_assert(sizeof(Cand) == 32, "cand size");
 
-constexpr size_t ANI_SMEM_SLABS = sizeof(WarpSlab) * ANI_WARPS;           // 163840
-constexpr size_t ANI_SMEM_CANDS = sizeof(Cand) * MAXP;                    // 32768
-constexpr size_t ANI_SMEM_BYTES = ANI_SMEM_SLABS + ANI_SMEM_CANDS + 256;  // + control block
-// after the chunk phase the slab area is reused: sort keys | state | chunk accumulators
-constexpr size_t FIN_KEYS_OFF = 0;                        // uint64_t[MAXP]
-constexpr size_t FIN_STATE_OFF = FIN_KEYS_OFF + 8 * MAXP; // uint8_t[MAXP]
-constexpr size_t FIN_ACC_OFF = FIN_STATE_OFF + MAXP;      // uint32_t A[nch], S[nch]
-constexpr uint32_t MAX_CHUNKS_PER_GENOME = (uint32_t)((ANI_SMEM_SLABS - FIN_ACC_OFF) / 8);
-
-struct AniCtl {
-    int n_cand;
-    int next_pair;
-    int unresolved;
-    int used;
-    unsigned long long span_q, span_r, a_tot, s_tot;
-    double sw, sx;
-};
-
-// warp-level bitonic sort of n (<= MAXA) 64-bit keys in shared memory, ascending
-__device__ __forceinline__ void warp_sort_keys(uint64_t *key, int n, int lane) {
-    int m = 1;
-    while (m < n) m <<= 1;
-    for (int i = n + lane; i < m; i += 32) key[i] = ~0ull;
-    __syncwarp();
-    for (int k = 2; k <= m; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (m >> 1); t += 32) {
-                // t-th compare-exchange of this stage: i has bit j clear
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const bool up = (i & k) == 0;
-                const uint64_t a = key[i], b = key[p];
-                if ((a > b) == up) {
-                    key[i] = b;
-                    key[p] = a;
-                }
-            }
-            __syncwarp();
-        }
-    }
+// roles + chunk count per pair (one thread per pair)
+__global__ void pair_setup_kernel(DbView db, const unsigned long long *__restrict__ pairs, int64_t n_pairs,
+                                  PairInfo *__restrict__ info, uint32_t *__restrict__ nch_out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t ga = (uint32_t)(pairs[p] >> 32), gb = (uint32_t)(pairs[p] & 0xffffffffu);
+    const uint64_t nsa = db.g_seed_off[ga + 1] - db.g_seed_off[ga];
+    const uint64_t nsb = db.g_seed_off[gb + 1] - db.g_seed_off[gb];
+    PairInfo pi;
+    pi.swapped = nsb < nsa;  // query = genome with fewer seeds (ties: a)
+    pi.q = pi.swapped ? gb : ga;
+    pi.r = pi.swapped ? ga : gb;
+    pi.nch = db.g_chunk_off[pi.q + 1] - db.g_chunk_off[pi.q];
+    info[p] = pi;
+    nch_out[p] = pi.nch;
 }
 
-// One query chunk against one reference index.  Appends up to chunk_cap candidates to cands[].
-__device__ __forceinline__ void process_chunk(const AniParams &prm, WarpSlab &w, int lane,
-                                              const uint64_t *__restrict__ qs /* chunk's seeds */, int nseeds,
-                                              uint32_t chunk_id, uint32_t chunk_start,
-                                              const uint64_t *__restrict__ T, uint32_t tmask, int tbits,
-                                              int chunk_cap, Cand *cands, int *n_cand) {
-    if (nseeds <= 0) return;
-    uint64_t *stage = reinterpret_cast<uint64_t *>(w.bor);  // [32][STAGE]
-    // ---- 1. anchors.  Optimistic pass with the full multiplicity cap; per-level tallies tell
-    //         whether a lower cap is needed to fit MAXA (oracle: halve until it fits).
-    int mult = prm.max_mult;
-    int n = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        int tally[4] = {0, 0, 0, 0};  // anchors if the cap were max_mult >> lv
-        int base = 0;
-        for (int s0 = 0; s0 < nseeds; s0 += 32) {
-            const int s = s0 + lane;
-            int c = 0;
-            uint64_t sd = 0;
-            if (s < nseeds) {
-                sd = qs[s];
-                if (!seed_rep(sd)) {
-                    const uint32_t km = seed_kmer(sd);
-                    uint32_t h = tab_slot(km, tbits);
-                    for (;;) {
-                        const uint64_t e = __ldg(T + h);
-                        if (e == TAB_EMPTY) break;
-                        if (seed_kmer(e) == km) {
-                            if (c < STAGE)
-                                stage[lane * STAGE + c] = ((uint64_t)seed_pos(e) << 32) |
-                                                          ((uint64_t)seed_pos(sd) << 1) |
-                                                          (uint64_t)(seed_strand(e) != seed_strand(sd));
-                            c++;
-                            if (c > prm.max_mult) break;
+__global__ void __launch_bounds__(CH_THREADS)
+chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
+             int64_t n_pairs, uint32_t n_tasks, Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
+    __shared__ GroupSlab slabs[CH_GROUPS];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (GRP - 1);                       // lane within group
+    const unsigned gmask = 0xffffu << (lane & GRP);        // lanes of this group
+    const int gbase = lane & GRP;                          // first lane of the group inside the warp
+    GroupSlab &w = slabs[threadIdx.x / GRP];
+    uint32_t *stage = w.bor;                               // [GRP][STAGE] (ref_pos << 1 | strand relation)
+    const uint32_t groups_total = gridDim.x * CH_GROUPS;
+    const uint32_t rounds = (n_tasks + groups_total - 1) / groups_total;
+
+    for (uint32_t round = 0; round < rounds; round++) {
+        const uint32_t t = round * groups_total + blockIdx.x * CH_GROUPS + threadIdx.x / GRP;
+        __syncwarp();  // both groups of the warp start a task together
+        if (t >= n_tasks) continue;
+        // ---- task -> (pair, chunk)
+        int64_t lo = 0, hi = n_pairs - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (task_off[mid] <= t)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const PairInfo pi = info[lo];
+        const uint32_t ch = t - task_off[lo];
+        const uint32_t choff = db.g_chunk_off[pi.q];
+        const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
+        const uint32_t sb = cbeg[ch], se = cbeg[ch + 1];
+        const int nseeds = (int)(se - sb);
+        if (nseeds <= 0) continue;
+        const uint64_t *qs = db.seeds + db.g_seed_off[pi.q] + sb;
+        const uint32_t cstart = db.chunk_start[choff + ch];
+        const uint64_t *T = db.tab + db.g_tab_off[pi.r];
+        const int tbits = db.g_tab_bits[pi.r];
+        const uint32_t tmask = (1u << tbits) - 1;
+
+        // ---- 1. anchors in query order.  Optimistic pass with the full multiplicity cap; per-level
+        //         tallies tell whether a lower cap is needed to fit MAXA (oracle: halve until it fits).
+        int mult = prm.max_mult, n = 0;
+        bool give_up = false;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            int tally[4] = {0, 0, 0, 0};
+            int base = 0;
+            for (int s0 = 0; s0 < nseeds; s0 += GRP) {
+                const int s = s0 + gl;
+                int c = 0;
+                uint64_t sd = 0;
+                if (s < nseeds) {
+                    sd = qs[s];
+                    if (!seed_rep(sd)) {
+                        const uint32_t km = seed_kmer(sd);
+                        uint32_t h = tab_slot(km, tbits);
+                        for (;;) {
+                            const uint64_t e = __ldg(T + h);
+                            if (e == TAB_EMPTY) break;
+                            if (seed_kmer(e) == km) {
+                                if (c < STAGE)
+                                    stage[gl * STAGE + c] = (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
+                                c++;
+                                if (c > prm.max_mult) break;
+                            }
+                            h = (h + 1) & tmask;
                         }
-                        h = (h + 1) & tmask;
+                    }
+                }
+                if (attempt == 0) {
+#pragma unroll
+                    for (int lv = 0; lv < 4; lv++)
+                        if (c >= 1 && c <= (prm.max_mult >> lv)) tally[lv] += c;
+                }
+                if (c > mult) c = 0;
+                if (c > 1) {  // hits of one seed in ascending ref position (insertion sort, c <= 8)
+                    for (int x = 1; x < c; x++) {
+                        const uint32_t v = stage[gl * STAGE + x];
+                        int y = x - 1;
+                        while (y >= 0 && stage[gl * STAGE + y] > v) {
+                            stage[gl * STAGE + y + 1] = stage[gl * STAGE + y];
+                            y--;
+                        }
+                        stage[gl * STAGE + y + 1] = v;
+                    }
+                }
+                int pre = c;
+#pragma unroll
+                for (int d = 1; d < GRP; d <<= 1) {
+                    const int u = __shfl_up_sync(gmask, pre, d, GRP);
+                    if (gl >= d) pre += u;
+                }
+                const int tot = __shfl_sync(gmask, pre, GRP - 1, GRP);
+                pre -= c;
+                const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
+                for (int x = 0; x < c; x++) {
+                    const int dst = base + pre + x;
+                    const uint32_t v = stage[gl * STAGE + x];
+                    if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
+                }
+                base += tot;
+            }
+            __syncwarp(gmask);
+            if (attempt == 1) {
+                n = base;
+                break;
+            }
+#pragma unroll
+            for (int lv = 0; lv < 4; lv++) tally[lv] = (int)__reduce_add_sync(gmask, (unsigned)tally[lv]);
+            if (tally[0] <= MAXA) {
+                n = tally[0];
+                break;
+            }
+            int lv = 1;
+            while (lv < 4 && (prm.max_mult >> lv) >= 1 && tally[lv] > MAXA) lv++;
+            if (lv >= 4 || (prm.max_mult >> lv) < 1) {
+                give_up = true;
+                break;
+            }
+            mult = prm.max_mult >> lv;
+        }
+        if (give_up || n < prm.min_anchors) continue;
+
+        // ---- 2. chaining DP in query order; lane gl keeps the latest anchor j with j % 16 == gl
+        uint64_t ra = 0;       // resident anchor
+        int rf = 0;            // its score
+        uint32_t rrc = 0;      // its (root << 9 | cnt)
+        for (int i = 0; i < n; i++) {
+            const uint64_t ai = w.anc[i];
+            const uint32_t ri = an_r(ai), qi = an_q(ai), revi = an_rev(ai);
+            const int dist = (i - 1 - gl) & (GRP - 1);  // this lane's j = i - 1 - dist
+            unsigned packed = 0;
+            if (dist < i) {
+                const uint32_t dq = qi - an_q(ra);
+                if (dq != 0 && dq <= (uint32_t)prm.band_bp && an_rev(ra) == revi) {
+                    const int dr = revi ? (int)an_r(ra) - (int)ri : (int)ri - (int)an_r(ra);
+                    if (dr > 0) {
+                        int gap = dr - (int)dq;
+                        gap = gap < 0 ? -gap : gap;
+                        if (gap <= prm.max_gap) {
+                            const int cand = rf + prm.anchor_score - gap;
+                            if (cand > prm.anchor_score) packed = ((unsigned)cand << 4) | (unsigned)(GRP - 1 - dist);
+                        }
                     }
                 }
             }
-            if (attempt == 0) {
-#pragma unroll
-                for (int lv = 0; lv < 4; lv++)
-                    if (c >= 1 && c <= (prm.max_mult >> lv)) tally[lv] += c;
-            }
-            if (c > mult) c = 0;
-            int pre = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, pre, d);
-                if (lane >= d) pre += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, pre, 31);
-            pre -= c;
-            for (int t = 0; t < c; t++) {
-                const int dst = base + pre + t;
-                if (dst < MAXA) w.key[dst] = stage[lane * STAGE + t];
-            }
-            base += tot;
-        }
-        __syncwarp();
-        if (attempt == 1) {
-            n = base;
-            break;
-        }
-#pragma unroll
-        for (int lv = 0; lv < 4; lv++) tally[lv] = (int)__reduce_add_sync(0xffffffffu, (unsigned)tally[lv]);
-        if (tally[0] <= MAXA) {
-            n = tally[0];
-            break;
-        }
-        int lv = 1;
-        while (lv < 4 && (prm.max_mult >> lv) >= 1 && tally[lv] > MAXA) lv++;
-        if (lv >= 4 || (prm.max_mult >> lv) < 1) return;  // nothing fits
-        mult = prm.max_mult >> lv;
-    }
-    if (n < prm.min_anchors) return;
-
-    // ---- 2. sort by (ref_pos, query_pos)
-    warp_sort_keys(w.key, n, lane);
-
-    // ---- 3. chaining DP (integer scores)
-    for (int i = 0; i < n; i++) {
-        const uint64_t ki = w.key[i];
-        const uint32_t ri = (uint32_t)(ki >> 32), qi = (uint32_t)(ki & 0xffffffffu) >> 1;
-        const uint32_t revi = (uint32_t)(ki & 1);
-        const int j = i - 1 - lane;
-        unsigned packed = 0;
-        if (j >= 0) {
-            const uint64_t kj = w.key[j];
-            const uint32_t rj = (uint32_t)(kj >> 32), qj = (uint32_t)(kj & 0xffffffffu) >> 1;
-            const uint32_t dr = ri - rj;
-            if (dr <= (uint32_t)prm.band_bp && dr != 0 && (uint32_t)(kj & 1) == revi) {
-                const int dq = revi ? (int)qj - (int)qi : (int)qi - (int)qj;
-                if (dq > 0) {
-                    int gap = (int)dr - dq;
-                    gap = gap < 0 ? -gap : gap;
-                    if (gap <= prm.max_gap) {
-                        const int cand = w.f[j] + prm.anchor_score - gap;
-                        if (cand > prm.anchor_score) packed = ((unsigned)cand << 5) | (unsigned)(31 - lane);
-                    }
-                }
-            }
-        }
-        const unsigned best = __reduce_max_sync(0xffffffffu, packed);
-        if (lane == 0) {
+            const unsigned best = __reduce_max_sync(gmask, packed);
+            int fi;
+            uint32_t rci;
             if (best) {
-                const int bj = i - 1 - (31 - (int)(best & 31));
-                w.f[i] = (int)(best >> 5);
-                w.root[i] = w.root[bj];
-                w.cnt[i] = w.cnt[bj] + 1;
+                const int bj = i - 1 - (GRP - 1 - (int)(best & (GRP - 1)));
+                const uint32_t rc = __shfl_sync(gmask, rrc, bj & (GRP - 1), GRP);
+                fi = (int)(best >> 4);
+                rci = rc + 1;  // same root, cnt + 1
             } else {
-                w.f[i] = prm.anchor_score;
-                w.root[i] = (uint16_t)i;
-                w.cnt[i] = 1;
+                fi = prm.anchor_score;
+                rci = ((uint32_t)i << 9) | 1u;
+            }
+            if (gl == (i & (GRP - 1))) {
+                ra = ai;
+                rf = fi;
+                rrc = rci;
+                w.res[i] = ((uint32_t)fi << 17) | rci;
             }
         }
-        __syncwarp();
-    }
+        __syncwarp(gmask);
 
-    // ---- 4. best end of every DP tree (ties: lowest index)
-    for (int i = lane; i < n; i += 32) w.bor[i] = 0;
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) atomicMax(&w.bor[w.root[i]], ((uint32_t)w.f[i] << 9) | (uint32_t)(MAXA - 1 - i));
-    __syncwarp();
-    // candidates owned by this lane: ends i == lane (mod 32) that qualify
-    uint32_t mine = 0;  // bit t <-> i = lane + 32 t
-    for (int i = lane, t = 0; i < n; i += 32, t++) {
-        const uint32_t pk = ((uint32_t)w.f[i] << 9) | (uint32_t)(MAXA - 1 - i);
-        if (w.bor[w.root[i]] == pk && w.cnt[i] >= prm.min_anchors && w.f[i] >= prm.min_score) mine |= 1u << t;
-    }
-    for (int round = 0; round < chunk_cap; round++) {
-        // lane-local best: smallest (16383 - score, q0 - chunk_start, r0)
-        uint64_t bk = ~0ull;
-        int bi = -1;
-        for (uint32_t mm = mine; mm; mm &= mm - 1) {
-            const int t = __ffs(mm) - 1, i = lane + 32 * t;
-            const int rt = w.root[i];
-            const uint64_t ke = w.key[i], kr = w.key[rt];
-            const uint32_t qe = (uint32_t)(ke & 0xffffffffu) >> 1, qr = (uint32_t)(kr & 0xffffffffu) >> 1;
-            const uint32_t q0 = qe < qr ? qe : qr;
-            const uint64_t k = ((uint64_t)(16383 - w.f[i]) << 47) | ((uint64_t)(q0 - chunk_start) << 32) |
-                               (uint64_t)(uint32_t)(kr >> 32);
-            if (k < bk) {
-                bk = k;
-                bi = i;
-            }
+        // ---- 3. best end of every DP tree (ties: lowest index), then the chunk's top candidates
+        for (int i = gl; i < n; i += GRP) w.bor[i] = 0;
+        __syncwarp(gmask);
+        for (int i = gl; i < n; i += GRP) {
+            const uint32_t x = w.res[i];
+            atomicMax(&w.bor[rs_root(x)], (rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i));
         }
-        const uint32_t hi = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32));
-        if (hi == 0xffffffffu) break;  // no candidate left in any lane
-        const uint32_t lo = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32) == hi ? (uint32_t)bk : 0xffffffffu);
-        const unsigned who = __ballot_sync(0xffffffffu, bk == (((uint64_t)hi << 32) | lo));
-        const int src = __ffs(who) - 1;
-        const int wi = __shfl_sync(0xffffffffu, bi, src);
-        const int rt = w.root[wi];
-        const uint64_t ke = w.key[wi], kr = w.key[rt];
-        const uint32_t qe = (uint32_t)(ke & 0xffffffffu) >> 1, qr = (uint32_t)(kr & 0xffffffffu) >> 1;
-        const uint32_t q0 = qe < qr ? qe : qr, q1 = qe < qr ? qr : qe;
-        // query seeds inside [q0, q1]
-        int cs = 0;
-        for (int s0 = 0; s0 < nseeds; s0 += 32) {
-            const int s = s0 + lane;
-            bool in = false;
-            if (s < nseeds) {
-                const uint32_t p = seed_pos(qs[s]);
-                in = p >= q0 && p <= q1;
-            }
-            cs += __popc(__ballot_sync(0xffffffffu, in));
+        __syncwarp(gmask);
+        uint32_t mine = 0;  // bit u <-> i = gl + 16 u
+        for (int i = gl, u = 0; i < n; i += GRP, u++) {
+            const uint32_t x = w.res[i];
+            if (w.bor[rs_root(x)] == ((rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i)) && (int)rs_cnt(x) >= prm.min_anchors &&
+                (int)rs_f(x) >= prm.min_score)
+                mine |= 1u << u;
         }
-        if (lane == src) {
-            mine &= ~(1u << ((wi - lane) >> 5));
-            const int idx = atomicAdd(n_cand, 1);
-            if (idx < MAXP) {
+        int n_out = 0;
+        for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
+            uint64_t bk = ~0ull;
+            int bi = -1;
+            for (uint32_t mm = mine; mm; mm &= mm - 1) {
+                const int i = gl + GRP * (__ffs(mm) - 1);
+                const uint32_t x = w.res[i];
+                const uint64_t ar = w.anc[rs_root(x)], ae = w.anc[i];
+                const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                const uint64_t k = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
+                if (k < bk) {
+                    bk = k;
+                    bi = i;
+                }
+            }
+            const uint32_t khi = __reduce_min_sync(gmask, (uint32_t)(bk >> 32));
+            if (khi == 0xffffffffu) break;
+            const uint32_t klo = __reduce_min_sync(gmask, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
+            const unsigned who = __ballot_sync(gmask, bk == (((uint64_t)khi << 32) | klo)) & gmask;
+            const int src = __ffs(who) - 1;  // absolute lane in warp
+            if (lane == src) {
+                mine &= ~(1u << ((bi - gl) / GRP));
+                const uint32_t x = w.res[bi];
+                const uint64_t ar = w.anc[rs_root(x)], ae = w.anc[bi];
                 Cand c;
-                c.q0 = q0;
-                c.q1 = q1;
-                c.r0 = (uint32_t)(kr >> 32);
-                c.r1 = (uint32_t)(ke >> 32);
-                c.chunk = chunk_id;
-                c.score = (uint16_t)w.f[wi];
-                c.n_anchors = w.cnt[wi];
-                c.n_seeds = (uint16_t)cs;
-                c.ordinal = (uint8_t)round;
-                c.rev = (uint8_t)(ke & 1);
+                c.q0 = cstart + an_q(ar);
+                c.q1 = cstart + an_q(ae);
+                c.r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                c.r1 = an_r(ar) < an_r(ae) ? an_r(ae) : an_r(ar);
+                c.chunk = ch;
+                c.score = (uint16_t)rs_f(x);
+                c.n_anchors = (uint16_t)rs_cnt(x);
+                c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
+                c.ordinal = (uint8_t)rnd;
+                c.rev = (uint8_t)an_rev(ae);
                 c.pad = 0;
-                cands[idx] = c;
+                cands[(size_t)t * SLOTS + rnd] = c;
             }
+            n_out++;
         }
+        if (gl == 0 && n_out) task_ncand[t] = (uint8_t)n_out;
+        (void)gbase;
     }
-    __syncwarp();
 }
 
-__device__ __forceinline__ double block_sum(double v, double *scratch /* [ANI_WARPS] */, int tid) {
+__device__ __forceinline__ double block_sum(double v, double *scratch /* [FIN_THREADS/32] */, int tid) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
     __syncthreads();
     if ((tid & 31) == 0) scratch[tid >> 5] = v;
     __syncthreads();
     double r = 0;
-    for (int i = 0; i < ANI_WARPS; i++) r += scratch[i];  // fixed order: deterministic
+    for (int i = 0; i < FIN_THREADS / 32; i++) r += scratch[i];  // fixed order: deterministic
     return r;
 }
 
-__global__ void __launch_bounds__(ANI_THREADS, 1)
-ani_pair_kernel(DbView db, AniParams prm, const unsigned long long *__restrict__ pairs, int64_t n_pairs,
-                PairOut *__restrict__ out, int *work_counter) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    WarpSlab *slabs = reinterpret_cast<WarpSlab *>(smem);
-    Cand *cands = reinterpret_cast<Cand *>(smem + ANI_SMEM_SLABS);
-    AniCtl *ctl = reinterpret_cast<AniCtl *>(smem + ANI_SMEM_SLABS + ANI_SMEM_CANDS);
-    double *red = reinterpret_cast<double *>(smem + ANI_SMEM_SLABS + ANI_SMEM_CANDS + 96);  // [16]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+struct FinCtl {
+    int n_cand, unresolved, n_acc, pad;
+    unsigned long long span_q, span_r, a_tot, s_tot;
+    double red[FIN_THREADS / 32];
+};
 
+// dynamic smem: Cand[MAXP] | uint64 keys[MAXP] | uint8 state[MAXP] | uint32 accA[nch], accS[nch]
+constexpr size_t FIN_SMEM_FIXED = sizeof(Cand) * MAXP + 8 * MAXP + MAXP;
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
+                int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
+                PairOut *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FinCtl ctl;
+    Cand *cands = reinterpret_cast<Cand *>(smem);
+    uint64_t *skey = reinterpret_cast<uint64_t *>(smem + sizeof(Cand) * MAXP);
+    uint8_t *state = smem + sizeof(Cand) * MAXP + 8 * MAXP;
+    uint32_t *accA = reinterpret_cast<uint32_t *>(smem + FIN_SMEM_FIXED);
+    const int tid = threadIdx.x;
+    const int64_t p = blockIdx.x;
+    if (p >= n_pairs) return;
+    const PairInfo pi = info[p];
+    const uint32_t nch = pi.nch, t0 = task_off[p];
+    const uint32_t choff = db.g_chunk_off[pi.q];
+    uint32_t *accS = accA + nch;
+    int overflow = nch > FIN_MAX_CHUNKS;
+    // ---- how many candidates per chunk may stay so that the pair fits MAXP (oracle: halve the cap)
+    int cap = overflow ? 0 : prm.max_chunk_chains;
+    while (cap > 0) {
+        int local = 0;
+        for (uint32_t ch = tid; ch < nch; ch += FIN_THREADS) {
+            const int c = task_ncand[t0 + ch];
+            local += c < cap ? c : cap;
+        }
+        const int total = (int)block_sum((double)local, ctl.red, tid);
+        if (total <= MAXP) break;
+        cap >>= 1;
+        if (cap == 0) overflow = 1;
+    }
+    if (tid == 0) {
+        ctl.n_cand = 0;
+        ctl.span_q = ctl.span_r = ctl.a_tot = ctl.s_tot = 0;
+        ctl.n_acc = 0;
+    }
+    for (uint32_t i = tid; i < 2 * nch && !overflow; i += FIN_THREADS) accA[i] = 0;
+    __syncthreads();
+    for (uint32_t ch = tid; ch < nch && cap > 0; ch += FIN_THREADS) {
+        int c = task_ncand[t0 + ch];
+        c = c < cap ? c : cap;
+        if (c) {
+            const int at = atomicAdd(&ctl.n_cand, c);
+            for (int x = 0; x < c; x++) cands[at + x] = gcands[(size_t)(t0 + ch) * SLOTS + x];
+        }
+    }
+    __syncthreads();
+    const int nc = ctl.n_cand;
+    int m = 1;
+    while (m < nc) m <<= 1;
+    for (int i = tid; i < m; i += FIN_THREADS) {
+        if (i < nc) {
+            const Cand &c = cands[i];
+            skey[i] = ((uint64_t)(16383 - c.score) << 48) | ((uint64_t)c.chunk << 16) | ((uint64_t)c.ordinal << 12) |
+                      (uint64_t)i;
+        } else
+            skey[i] = ~0ull;
+        state[i] = 0;
+    }
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (m >> 1); t += FIN_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int q = i | j;
+                const bool up = (i & k) == 0;
+                const uint64_t a = skey[i], b = skey[q];
+                if ((a > b) == up) {
+                    skey[i] = b;
+                    skey[q] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // greedy non-overlap selection, resolved in parallel rounds.
+    // state: 0 unknown, 1 accepted, 2 rejected.  The candidate at sorted rank t is accepted iff no
+    // ACCEPTED candidate of lower rank overlaps more than ovl_num/ovl_den of ITS length on query or ref.
     for (;;) {
         __syncthreads();
-        if (tid == 0) ctl->next_pair = atomicAdd(work_counter, 1);
+        if (tid == 0) ctl.unresolved = 0;
         __syncthreads();
-        const int64_t pi = ctl->next_pair;
-        if (pi >= n_pairs) return;
-        const uint32_t ga = (uint32_t)(pairs[pi] >> 32), gb = (uint32_t)(pairs[pi] & 0xffffffffu);
-        const uint64_t nsa = db.g_seed_off[ga + 1] - db.g_seed_off[ga];
-        const uint64_t nsb = db.g_seed_off[gb + 1] - db.g_seed_off[gb];
-        const int swapped = nsb < nsa;  // query = genome with fewer seeds (ties: a)
-        const uint32_t gq = swapped ? gb : ga, gr = swapped ? ga : gb;
-        const uint64_t *qseeds = db.seeds + db.g_seed_off[gq];
-        const uint32_t choff = db.g_chunk_off[gq];
-        const uint32_t nch = db.g_chunk_off[gq + 1] - choff;
-        const uint32_t *cbeg = db.chunk_begin + choff + gq;
-        const uint64_t *T = db.tab + db.g_tab_off[gr];
-        const int tbits = db.g_tab_bits[gr];
-        const uint32_t tmask = (1u << tbits) - 1;
-
-        int overflow = 0;
-        int chunk_cap = prm.max_chunk_chains;
-        if (nch > MAX_CHUNKS_PER_GENOME) {
-            overflow = 1;
-            chunk_cap = 0;
-        }
-        // ---- chunk phase (retry with a halved per-chunk cap if the pair overflows MAXP)
-        while (chunk_cap > 0) {
-            if (tid == 0) ctl->n_cand = 0;
-            __syncthreads();
-            for (uint32_t ch = warp; ch < nch; ch += ANI_WARPS) {
-                const uint32_t sb = cbeg[ch], se = cbeg[ch + 1];
-                process_chunk(prm, slabs[warp], lane, qseeds + sb, (int)(se - sb), ch, db.chunk_start[choff + ch], T,
-                              tmask, tbits, chunk_cap, cands, &ctl->n_cand);
-            }
-            __syncthreads();
-            if (ctl->n_cand <= MAXP) break;
-            chunk_cap >>= 1;
-            if (chunk_cap == 0) overflow = 1;
-            __syncthreads();
-        }
-        const int nc = (chunk_cap > 0) ? ctl->n_cand : 0;
-        __syncthreads();
-
-        // ---- finalize: slab area is free now
-        uint64_t *skey = reinterpret_cast<uint64_t *>(smem + FIN_KEYS_OFF);
-        uint8_t *state = smem + FIN_STATE_OFF;
-        uint32_t *accA = reinterpret_cast<uint32_t *>(smem + FIN_ACC_OFF);
-        uint32_t *accS = accA + nch;
-        int m = 1;
-        while (m < nc) m <<= 1;
-        for (int i = tid; i < m; i += ANI_THREADS) {
-            if (i < nc) {
-                const Cand &c = cands[i];
-                skey[i] = ((uint64_t)(16383 - c.score) << 48) | ((uint64_t)c.chunk << 16) |
-                          ((uint64_t)c.ordinal << 12) | (uint64_t)i;
-            } else
-                skey[i] = ~0ull;
-            state[i] = 0;
-        }
-        for (uint32_t i = tid; i < 2 * nch; i += ANI_THREADS) accA[i] = 0;
-        if (tid == 0) {
-            ctl->span_q = ctl->span_r = ctl->a_tot = ctl->s_tot = 0;
-            ctl->used = 0;
-        }
-        __syncthreads();
-        // block bitonic sort of skey[0..m)
-        for (int k = 2; k <= m; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (m >> 1); t += ANI_THREADS) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int p = i | j;
-                    const bool up = (i & k) == 0;
-                    const uint64_t a = skey[i], b = skey[p];
-                    if ((a > b) == up) {
-                        skey[i] = b;
-                        skey[p] = a;
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        // greedy non-overlap selection, resolved in parallel rounds.
-        // state: 0 unknown, 1 accepted, 2 rejected.  Candidate at sorted rank t is accepted iff no
-        // ACCEPTED candidate of lower rank overlaps more than ovl_num/ovl_den of ITS length on query or ref.
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) ctl->unresolved = 0;
-            __syncthreads();
-            for (int t = tid; t < nc; t += ANI_THREADS) {
-                if (state[t]) continue;
-                const Cand &c = cands[(int)(skey[t] & 0xfff)];
-                const long long lq = (long long)c.q1 - c.q0 + 1, lr = (long long)c.r1 - c.r0 + 1;
-                int verdict = 1;
-                for (int u = 0; u < t; u++) {
-                    const uint8_t su = ((volatile uint8_t *)state)[u];
-                    if (su == 2) continue;
-                    const Cand &d = cands[(int)(skey[u] & 0xfff)];
-                    const long long oq = (long long)(c.q1 < d.q1 ? c.q1 : d.q1) - (long long)(c.q0 > d.q0 ? c.q0 : d.q0) + 1;
-                    const long long orr = (long long)(c.r1 < d.r1 ? c.r1 : d.r1) - (long long)(c.r0 > d.r0 ? c.r0 : d.r0) + 1;
-                    const bool blocks = (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) ||
-                                        (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
-                    if (!blocks) continue;
-                    if (su == 1) {
-                        verdict = 2;
-                        break;
-                    }
-                    verdict = 0;  // blocked by an undecided candidate: wait
-                }
-                if (verdict)
-                    ((volatile uint8_t *)state)[t] = (uint8_t)verdict;
-                else
-                    ctl->unresolved = 1;
-            }
-            __syncthreads();
-            if (!ctl->unresolved) break;
-        }
-        // accumulate accepted chains
-        const uint32_t rcoff = db.g_ctg_off[gr];
-        const int nrc = (int)(db.g_ctg_off[gr + 1] - rcoff);
-        int n_acc_local = 0;
-        for (int t = tid; t < nc; t += ANI_THREADS) {
-            if (state[t] != 1) continue;
-            n_acc_local++;
+        for (int t = tid; t < nc; t += FIN_THREADS) {
+            if (state[t]) continue;
             const Cand &c = cands[(int)(skey[t] & 0xfff)];
-            atomicAdd(&accA[c.chunk], (uint32_t)c.n_anchors);
-            atomicAdd(&accS[c.chunk], (uint32_t)c.n_seeds);
-            const long long e = prm.span_ext, k1 = K_SEED - 1;
-            const long long cs = db.chunk_start[choff + c.chunk], ce = cs + db.chunk_len[choff + c.chunk] - 1;
-            long long a0 = (long long)c.q0 - k1 - e, a1 = (long long)c.q1 + e;
-            a0 = a0 < cs ? cs : a0;
-            a1 = a1 > ce ? ce : a1;
-            int lo = 0, hi = nrc - 1;  // reference contig holding r0
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (db.ctg_pstart[rcoff + mid] <= c.r0)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const long long rs = db.ctg_pstart[rcoff + lo], re = rs + db.ctg_len[rcoff + lo] - 1;
-            long long b0 = (long long)c.r0 - k1 - e, b1 = (long long)c.r1 + e;
-            b0 = b0 < rs ? rs : b0;
-            b1 = b1 > re ? re : b1;
-            atomicAdd(&ctl->span_q, (unsigned long long)(a1 - a0 + 1));
-            atomicAdd(&ctl->span_r, (unsigned long long)(b1 - b0 + 1));
-            atomicAdd(&ctl->a_tot, (unsigned long long)c.n_anchors);
-            atomicAdd(&ctl->s_tot, (unsigned long long)c.n_seeds);
-        }
-        if (n_acc_local) atomicAdd(&ctl->used, n_acc_local);  // chains accepted
-        __syncthreads();
-        // per-chunk ANI, seed-weighted mean
-        double sw = 0, sx = 0;
-        int used = 0;
-        for (uint32_t ch = tid; ch < nch; ch += ANI_THREADS) {
-            const uint32_t A = accA[ch], S = accS[ch];
-            if ((int)S < prm.min_chunk_seeds || A == 0) continue;
-            double ratio = (double)A / (double)S;
-            if (ratio > 1.0) ratio = 1.0;
-            const double x = pow(ratio, 1.0 / (double)K_SEED);
-            sw += (double)S;
-            sx += (double)S * x;
-            used++;
-        }
-        sw = block_sum(sw, red, tid);
-        sx = block_sum(sx, red, tid);
-        const double usedd = block_sum((double)used, red, tid);
-        if (tid == 0) {
-            PairOut o;
-            o.ani = o.ani_raw = -1.0;
-            o.af_q = o.af_r = 0.0;
-            o.n_anchors = (int64_t)ctl->a_tot;
-            o.n_seeds = (int64_t)ctl->s_tot;
-            o.span_q = (int64_t)ctl->span_q;
-            o.span_r = (int64_t)ctl->span_r;
-            o.n_chains = ctl->used;
-            o.n_chunks_used = (int)usedd;
-            o.swapped = swapped;
-            o.overflow = overflow;
-            if (usedd > 0 && sw > 0) {
-                const double mean = sx / sw;
-                o.ani_raw = mean;
-                double afq = (double)o.span_q / (double)db.g_total_len[gq];
-                double afr = (double)o.span_r / (double)db.g_total_len[gr];
-                o.af_q = afq > 1.0 ? 1.0 : afq;
-                o.af_r = afr > 1.0 ? 1.0 : afr;
-                const double x = 100.0 * (1.0 - mean);
-                double ani = 1.0;
-                if (x > 0.0) {
-                    ani = 1.0 - prm.debias_a * pow(x, prm.debias_g) / 100.0;
-                    if (ani < 0.0) ani = 0.0;
+            const long long lq = (long long)c.q1 - c.q0 + 1, lr = (long long)c.r1 - c.r0 + 1;
+            int verdict = 1;
+            for (int u = 0; u < t; u++) {
+                const uint8_t su = ((volatile uint8_t *)state)[u];
+                if (su == 2) continue;
+                const Cand &d = cands[(int)(skey[u] & 0xfff)];
+                const long long oq = (long long)(c.q1 < d.q1 ? c.q1 : d.q1) - (long long)(c.q0 > d.q0 ? c.q0 : d.q0) + 1;
+                const long long orr = (long long)(c.r1 < d.r1 ? c.r1 : d.r1) - (long long)(c.r0 > d.r0 ? c.r0 : d.r0) + 1;
+                const bool blocks = (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) ||
+                                    (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
+                if (!blocks) continue;
+                if (su == 1) {
+                    verdict = 2;
+                    break;
                 }
-                o.ani = ani > 1.0 ? 1.0 : ani;
+                verdict = 0;  // blocked by an undecided candidate: wait
             }
-            out[pi] = o;
+            if (verdict)
+                ((volatile uint8_t *)state)[t] = (uint8_t)verdict;
+            else
+                ctl.unresolved = 1;
         }
+        __syncthreads();
+        if (!ctl.unresolved) break;
+    }
+    // accumulate accepted chains
+    const uint32_t rcoff = db.g_ctg_off[pi.r];
+    const int nrc = (int)(db.g_ctg_off[pi.r + 1] - rcoff);
+    int n_acc_local = 0;
+    for (int t = tid; t < nc; t += FIN_THREADS) {
+        if (state[t] != 1) continue;
+        n_acc_local++;
+        const Cand &c = cands[(int)(skey[t] & 0xfff)];
+        atomicAdd(&accA[c.chunk], (uint32_t)c.n_anchors);
+        atomicAdd(&accS[c.chunk], (uint32_t)c.n_seeds);
+        const long long e = prm.span_ext, k1 = K_SEED - 1;
+        const long long cs = db.chunk_start[choff + c.chunk], ce = cs + db.chunk_len[choff + c.chunk] - 1;
+        long long a0 = (long long)c.q0 - k1 - e, a1 = (long long)c.q1 + e;
+        a0 = a0 < cs ? cs : a0;
+        a1 = a1 > ce ? ce : a1;
+        int lo = 0, hi = nrc - 1;  // reference contig holding r0
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (db.ctg_pstart[rcoff + mid] <= c.r0)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const long long rs = db.ctg_pstart[rcoff + lo], re = rs + db.ctg_len[rcoff + lo] - 1;
+        long long b0 = (long long)c.r0 - k1 - e, b1 = (long long)c.r1 + e;
+        b0 = b0 < rs ? rs : b0;
+        b1 = b1 > re ? re : b1;
+        atomicAdd(&ctl.span_q, (unsigned long long)(a1 - a0 + 1));
+        atomicAdd(&ctl.span_r, (unsigned long long)(b1 - b0 + 1));
+        atomicAdd(&ctl.a_tot, (unsigned long long)c.n_anchors);
+        atomicAdd(&ctl.s_tot, (unsigned long long)c.n_seeds);
+    }
+    if (n_acc_local) atomicAdd(&ctl.n_acc, n_acc_local);
+    __syncthreads();
+    // per-chunk ANI, seed-weighted mean
+    double sw = 0, sx = 0;
+    int used = 0;
+    for (uint32_t ch = tid; ch < nch && !overflow; ch += FIN_THREADS) {
+        const uint32_t A = accA[ch], S = accS[ch];
+        if ((int)S < prm.min_chunk_seeds || A == 0) continue;
+        double ratio = (double)A / (double)S;
+        if (ratio > 1.0) ratio = 1.0;
+        const double x = pow(ratio, 1.0 / (double)K_SEED);
+        sw += (double)S;
+        sx += (double)S * x;
+        used++;
+    }
+    sw = block_sum(sw, ctl.red, tid);
+    sx = block_sum(sx, ctl.red, tid);
+    const double usedd = block_sum((double)used, ctl.red, tid);
+    if (tid == 0) {
+        PairOut o;
+        o.ani = o.ani_raw = -1.0;
+        o.af_q = o.af_r = 0.0;
+        o.n_anchors = (int64_t)ctl.a_tot;
+        o.n_seeds = (int64_t)ctl.s_tot;
+        o.span_q = (int64_t)ctl.span_q;
+        o.span_r = (int64_t)ctl.span_r;
+        o.n_chains = ctl.n_acc;
+        o.n_chunks_used = (int)usedd;
+        o.swapped = (int32_t)pi.swapped;
+        o.overflow = overflow;
+        if (usedd > 0 && sw > 0) {
+            const double mean = sx / sw;
+            o.ani_raw = mean;
+            double afq = (double)o.span_q / (double)db.g_total_len[pi.q];
+            double afr = (double)o.span_r / (double)db.g_total_len[pi.r];
+            o.af_q = afq > 1.0 ? 1.0 : afq;
+            o.af_r = afr > 1.0 ? 1.0 : afr;
+            const double x = 100.0 * (1.0 - mean);
+            double ani = 1.0;
+            if (x > 0.0) {
+                ani = 1.0 - prm.debias_a * pow(x, prm.debias_g) / 100.0;
+                if (ani < 0.0) ani = 0.0;
+            }
+            o.ani = ani > 1.0 ? 1.0 : ani;
+        }
+        out[p] = o;
     }
 }
 
@@ -533,6 +555,27 @@ __global__ void edge_compact_kernel(const unsigned long long *__restrict__ pairs
     if (lane == 0) base = atomicAdd(n_edges, (unsigned long long)__popc(bal));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) edges[base + __popc(bal & ((1u << lane) - 1))] = e;
+}
+
+// roofline bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors
+__global__ void pair_sums_kernel(const PairInfo *__restrict__ info, const PairOut *__restrict__ po, int64_t n_pairs,
+                                 const uint64_t *__restrict__ g_seed_off, unsigned long long *sums /* [2] */) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sq = 0, an = 0;
+    if (t < n_pairs) {
+        const uint32_t q = info[t].q;
+        sq = g_seed_off[q + 1] - g_seed_off[q];
+        an = (unsigned long long)po[t].n_anchors;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sq += __shfl_down_sync(0xffffffffu, sq, d);
+        an += __shfl_down_sync(0xffffffffu, an, d);
+    }
+    if ((threadIdx.x & 31) == 0 && (sq | an)) {
+        atomicAdd(&sums[0], sq);
+        atomicAdd(&sums[1], an);
+    }
 }
 
 }  // namespace skb

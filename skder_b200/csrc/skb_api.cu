@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,23 @@ struct DevBuf {
     }
 };
 
+// Typed view of a persistent, grow-only scratch buffer owned by the context: the steady state of
+// every entry point performs no cudaMalloc/cudaFree.
+template <typename T>
+struct PoolRef {
+    DevBuf<unsigned char> &b;
+    T *p;
+    explicit PoolRef(DevBuf<unsigned char> &buf) : b(buf), p(reinterpret_cast<T *>(buf.p)) {}
+    void reserve(size_t n, size_t keep, cudaStream_t st) {
+        b.reserve(n * sizeof(T), keep * sizeof(T), st);
+        p = reinterpret_cast<T *>(b.p);
+    }
+    void upload(const std::vector<T> &h, cudaStream_t st) {
+        reserve(std::max<size_t>(h.size(), 1), 0, st);
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
 inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -76,6 +94,7 @@ struct skb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     bool ani_attr_set = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 
     // ---- sketch DB (host metadata)
     std::vector<uint64_t> h_seed_off{0};   // [n+1]
@@ -97,7 +116,12 @@ struct skb_ctx {
     uint64_t n_inv = 0;
     // scratch
     DevBuf<unsigned char> d_tmp;
+    std::map<std::string, DevBuf<unsigned char>> pool;  // named scratch, see PoolRef
     DevBuf<int> d_counter;
+    DevBuf<PairInfo> d_info;
+    DevBuf<uint32_t> d_nch, d_task_off;
+    DevBuf<Cand> d_cands;
+    DevBuf<uint8_t> d_task_ncand;
 
     int32_t n() const { return (int32_t)h_total_len.size(); }
     DbView view() const {
@@ -202,8 +226,8 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     }
     const uint32_t n_tiles = tile_off[nb];
     const size_t n_warps = (size_t)n_tiles * SK_WARPS;
-    DevBuf<uint64_t> d_packed, d_word_off, d_nbases, d_ctg_start;
-    DevBuf<uint32_t> d_ctg_off, d_tile_off, d_cnt_s, d_cnt_m, d_off_s, d_off_m;
+    PoolRef<uint64_t> d_packed(c->pool["sketch_batch.d_packed"]), d_word_off(c->pool["sketch_batch.d_word_off"]), d_nbases(c->pool["sketch_batch.d_nbases"]), d_ctg_start(c->pool["sketch_batch.d_ctg_start"]);
+    PoolRef<uint32_t> d_ctg_off(c->pool["sketch_batch.d_ctg_off"]), d_tile_off(c->pool["sketch_batch.d_tile_off"]), d_cnt_s(c->pool["sketch_batch.d_cnt_s"]), d_cnt_m(c->pool["sketch_batch.d_cnt_m"]), d_off_s(c->pool["sketch_batch.d_off_s"]), d_off_m(c->pool["sketch_batch.d_off_m"]);
     d_packed.reserve(word_off[nb] + 2, 0, c->st);
     for (int32_t i = 0; i < nb; i++)
         CK(cudaMemcpyAsync(d_packed.p + word_off[i], gen[g0 + i]->words, (size_t)gen[g0 + i]->n_words * 8,
@@ -261,35 +285,76 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
 }
 
 // ---- ANI over a device-resident pair list --------------------------------------------------------
+// Scratch of the pair stage, kept across calls (no cudaMalloc/cudaFree in the steady state).
+//   info      : roles and chunk count per pair
+//   task_off  : exclusive prefix of chunk counts -> task id = (pair, chunk)
+//   cands     : SLOTS candidate slots per task;  task_ncand: how many are filled
 void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, PairOut *d_out) {
     if (n_pairs == 0) return;
-    c->d_counter.reserve(4, 0, c->st);
-    CK(cudaMemsetAsync(c->d_counter.p, 0, sizeof(int), c->st));
+    if (n_pairs >= (1ll << 31)) throw CudaFail{"too many surviving pairs in one call"};
     if (!c->ani_attr_set) {
-        CK(cudaFuncSetAttribute(ani_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ANI_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS)));
         c->ani_attr_set = true;
     }
-    const int grid = (int)std::min<int64_t>(n_pairs, c->sm_count);
-    ani_pair_kernel<<<grid, ANI_THREADS, ANI_SMEM_BYTES, c->st>>>(c->view(), c->ani_params(), d_pairs, n_pairs, d_out,
-                                                                  c->d_counter.p);
+    const DbView view = c->view();
+    const AniParams prm = c->ani_params();
+    c->d_info.reserve((size_t)n_pairs, 0, c->st);
+    c->d_nch.reserve((size_t)n_pairs + 1, 0, c->st);
+    c->d_task_off.reserve((size_t)n_pairs + 1, 0, c->st);
+    pair_setup_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(view, d_pairs, n_pairs, c->d_info.p, c->d_nch.p);
     CK(cudaGetLastError());
     c->launches++;
+    // batches of pairs whose tasks fit the candidate scratch (<= 8 Mi tasks = 1 GiB of slots)
+    std::vector<uint32_t> h_nch((size_t)n_pairs);
+    CK(cudaMemcpyAsync(h_nch.data(), c->d_nch.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint64_t max_tasks = 8ull << 20;
+    int64_t p0 = 0;
+    while (p0 < n_pairs) {
+        uint64_t tasks = 0;
+        int64_t p1 = p0;
+        while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) tasks += h_nch[(size_t)p1++];
+        if (tasks >= (1ull << 32)) throw CudaFail{"pair with too many chunks"};
+        const int64_t np = p1 - p0;
+        CK(cudaMemsetAsync(c->d_nch.p + p1, 0, 4, c->st));  // sentinel for the scan (restored below)
+        exclusive_scan_u32(c, c->d_nch.p + p0, c->d_task_off.p, (size_t)np + 1);
+        if (p1 < n_pairs)
+            CK(cudaMemcpyAsync(c->d_nch.p + p1, &h_nch[(size_t)p1], 4, cudaMemcpyHostToDevice, c->st));
+        if (tasks) {
+            c->d_cands.reserve((size_t)tasks * SLOTS, 0, c->st);
+            c->d_task_ncand.reserve((size_t)tasks, 0, c->st);
+            CK(cudaMemsetAsync(c->d_task_ncand.p, 0, (size_t)tasks, c->st));
+            const unsigned want = nblk(tasks, CH_GROUPS);
+            const unsigned grid = std::min<unsigned>(want, (unsigned)c->sm_count * 7u * 4u);
+            chunk_kernel<<<grid, CH_THREADS, 0, c->st>>>(view, prm, c->d_info.p + p0, c->d_task_off.p, np,
+                                                        (uint32_t)tasks, c->d_cands.p, c->d_task_ncand.p);
+            CK(cudaGetLastError());
+            c->launches++;
+        }
+        finalize_kernel<<<(unsigned)np, FIN_THREADS, FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS, c->st>>>(
+            view, prm, c->d_info.p + p0, c->d_task_off.p, np, c->d_cands.p, c->d_task_ncand.p, d_out + p0);
+        CK(cudaGetLastError());
+        c->launches++;
+        p0 = p1;
+    }
 }
 
 struct EdgeRun {
     std::vector<skb_edge> edges;
     int64_t n_screened = 0;
     float ms_screen = 0, ms_ani = 0;
+    unsigned long long sums[2] = {0, 0};  // sum query seeds, sum anchors
 };
 
 // pairs on device -> ANI -> compacted edges on host
 void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, double min_af_pct, EdgeRun &run,
                     cudaEvent_t ev_mid, cudaEvent_t ev_end) {
-    DevBuf<PairOut> d_out;
-    DevBuf<skb_edge> d_edges;
-    DevBuf<unsigned long long> d_n;
-    d_n.reserve(1, 0, c->st);
-    CK(cudaMemsetAsync(d_n.p, 0, 8, c->st));
+    PoolRef<PairOut> d_out(c->pool["pairs_to_edges.d_out"]);
+    PoolRef<skb_edge> d_edges(c->pool["pairs_to_edges.d_edges"]);
+    PoolRef<unsigned long long> d_n(c->pool["pairs_to_edges.d_n"]);
+    d_n.reserve(3, 0, c->st);
+    CK(cudaMemsetAsync(d_n.p, 0, 24, c->st));
     CK(cudaEventRecord(ev_mid, c->st));
     unsigned long long ne = 0;
     if (n_pairs > 0) {
@@ -302,8 +367,18 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
         c->launches++;
     }
     CK(cudaEventRecord(ev_end, c->st));
-    CK(cudaMemcpyAsync(&ne, d_n.p, 8, cudaMemcpyDeviceToHost, c->st));
+    if (n_pairs > 0) {
+        pair_sums_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(c->d_info.p, d_out.p, n_pairs,
+                                                                         c->d_seed_off.p, d_n.p + 1);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    unsigned long long h3[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h3, d_n.p, 24, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    ne = h3[0];
+    run.sums[0] = h3[1];
+    run.sums[1] = h3[2];
     run.edges.resize((size_t)ne);
     if (ne) CK(cudaMemcpy(run.edges.data(), d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost));
     std::sort(run.edges.begin(), run.edges.end(), [](const skb_edge &x, const skb_edge &y) {
@@ -366,7 +441,7 @@ int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
         skb_default_params(&c->prm);
     const skb_params &p = c->prm;
     if (p.max_mult < 1 || p.max_mult > STAGE || (p.max_mult & (p.max_mult - 1)) || p.max_chunk_chains < 1 ||
-        p.max_chunk_chains > 8 || p.band_bp >= (int32_t)CONTIG_PAD || p.band_bp < 1 || p.chunk_len < 64 ||
+        p.max_chunk_chains > SLOTS || p.band_bp >= (int32_t)CONTIG_PAD || p.band_bp < 1 || p.chunk_len < 64 ||
         p.chunk_len > 32767 || p.anchor_score < 1 || p.anchor_score > 20 || p.ovl_den < 1) {
         g_create_error = "parameter outside the range the kernels support";
         delete c;
@@ -394,6 +469,8 @@ int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
 void skb_destroy(skb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->st) {
         cudaStreamSynchronize(ctx->st);
         cudaStreamDestroy(ctx->st);
@@ -406,6 +483,42 @@ int32_t skb_n_genomes(const skb_ctx *ctx) { return ctx ? ctx->n() : 0; }
 int64_t skb_launch_count(const skb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *skb_stream(const skb_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 void skb_free(void *p) { std::free(p); }
+
+int skb_clear(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
+        CK(cudaStreamSynchronize(ctx->st));
+        ctx->h_seed_off.assign(1, 0);
+        ctx->h_total_len.clear();
+        ctx->h_ctg_off.assign(1, 0);
+        ctx->h_ctg_len.clear();
+        ctx->n_mkeys = 0;
+        ctx->indexed = false;
+        ctx->n_indexed = 0;
+        ctx->n_inv = 0;
+        return SKB_OK;
+    });
+}
+
+int skb_timer_start(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->t0) {
+            CK(cudaEventCreate(&ctx->t0));
+            CK(cudaEventCreate(&ctx->t1));
+        }
+        CK(cudaEventRecord(ctx->t0, ctx->st));
+        return SKB_OK;
+    });
+}
+
+int skb_timer_stop(skb_ctx *ctx, float *ms) {
+    return guarded(ctx, [&]() -> int {
+        if (!ctx->t0 || !ms) return fail(ctx, SKB_ESTATE, "timer not started");
+        CK(cudaEventRecord(ctx->t1, ctx->st));
+        CK(cudaEventSynchronize(ctx->t1));
+        CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+        return SKB_OK;
+    });
+}
 
 int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
     return guarded(ctx, [&]() -> int {
@@ -502,8 +615,8 @@ int skb_index(skb_ctx *ctx) {
         c->h_marker_off.assign(n + 1, 0);
         if (c->n_mkeys) {
             if (c->n_mkeys >= (1ull << 32)) return fail(c, SKB_ELIMIT, "too many marker keys");
-            DevBuf<uint64_t> d_sorted;
-            DevBuf<uint32_t> d_flag, d_pos;
+            PoolRef<uint64_t> d_sorted(c->pool["skb_index.d_sorted"]);
+            PoolRef<uint32_t> d_flag(c->pool["skb_index.d_flag"]), d_pos(c->pool["skb_index.d_pos"]);
             d_sorted.reserve(c->n_mkeys, 0, c->st);
             d_flag.reserve(c->n_mkeys + 1, 0, c->st);
             d_pos.reserve(c->n_mkeys + 1, 0, c->st);
@@ -592,8 +705,8 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
         const uint32_t rows_local = (n > (uint32_t)part) ? (n - 1 - (uint32_t)part) / (uint32_t)n_parts + 1 : 0;
         int64_t pairs_total = 0;
         for (uint32_t a = (uint32_t)part; a < n; a += (uint32_t)n_parts) pairs_total += n - 1 - a;
-        DevBuf<uint32_t> d_cnt;
-        DevBuf<unsigned long long> d_pairs, d_pairs_sorted, d_np;
+        PoolRef<uint32_t> d_cnt(c->pool["skb_triangle.d_cnt"]);
+        PoolRef<unsigned long long> d_pairs(c->pool["skb_triangle.d_pairs"]), d_pairs_sorted(c->pool["skb_triangle.d_pairs_sorted"]), d_np(c->pool["skb_triangle.d_np"]);
         d_np.reserve(1, 0, c->st);
         CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
         const double scale = screen_pct > 0.0 ? std::pow(screen_pct / 100.0, (double)K_MARKER) : 0.0;
@@ -646,6 +759,8 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;
             stats->launches = c->launches - launches0;
+            stats->sum_query_seeds = (int64_t)run.sums[0];
+            stats->sum_anchors = (int64_t)run.sums[1];
         }
         return emit_edges(c, run, edges, n_edges);
     });
@@ -676,10 +791,10 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
         CK(cudaEventCreate(&e1));
         CK(cudaEventCreate(&e2));
         CK(cudaEventRecord(e0, c->st));
-        DevBuf<int32_t> d_refs, d_queries, d_slot;
-        DevBuf<uint64_t> d_qpref;
-        DevBuf<uint32_t> d_cnt;
-        DevBuf<unsigned long long> d_pairs, d_pairs_sorted, d_np;
+        PoolRef<int32_t> d_refs(c->pool["skb_rect.d_refs"]), d_queries(c->pool["skb_rect.d_queries"]), d_slot(c->pool["skb_rect.d_slot"]);
+        PoolRef<uint64_t> d_qpref(c->pool["skb_rect.d_qpref"]);
+        PoolRef<uint32_t> d_cnt(c->pool["skb_rect.d_cnt"]);
+        PoolRef<unsigned long long> d_pairs(c->pool["skb_rect.d_pairs"]), d_pairs_sorted(c->pool["skb_rect.d_pairs_sorted"]), d_np(c->pool["skb_rect.d_np"]);
         const uint64_t cells = (uint64_t)n_refs * (uint64_t)n_queries;
         unsigned long long np = 0;
         d_np.reserve(1, 0, c->st);
@@ -736,6 +851,8 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;
             stats->launches = c->launches - launches0;
+            stats->sum_query_seeds = (int64_t)run.sums[0];
+            stats->sum_anchors = (int64_t)run.sums[1];
         }
         return emit_edges(c, run, edges, n_edges);
     });
@@ -753,8 +870,8 @@ int skb_pairs_detail(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64_t
                 return fail(c, SKB_EINVAL, "pair id out of range");
             hp[(size_t)i] = ((unsigned long long)a[i] << 32) | b[i];
         }
-        DevBuf<unsigned long long> d_pairs;
-        DevBuf<PairOut> d_out;
+        PoolRef<unsigned long long> d_pairs(c->pool["skb_pairs_detail.d_pairs"]);
+        PoolRef<PairOut> d_out(c->pool["skb_pairs_detail.d_out"]);
         d_pairs.upload(hp, c->st);
         d_out.reserve((size_t)n, 0, c->st);
         run_ani(c, d_pairs.p, n, d_out.p);
@@ -792,8 +909,8 @@ int skb_shared_markers(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64
         for (int64_t i = 0; i < n; i++)
             if (a[i] >= (uint32_t)c->n_indexed || b[i] >= (uint32_t)c->n_indexed)
                 return fail(c, SKB_EINVAL, "pair id out of range");
-        DevBuf<uint32_t> da, db;
-        DevBuf<long long> dout;
+        PoolRef<uint32_t> da(c->pool["skb_shared_markers.da"]), db(c->pool["skb_shared_markers.db"]);
+        PoolRef<long long> dout(c->pool["skb_shared_markers.dout"]);
         da.upload(std::vector<uint32_t>(a, a + n), c->st);
         db.upload(std::vector<uint32_t>(b, b + n), c->st);
         dout.reserve((size_t)n, 0, c->st);

@@ -133,6 +133,17 @@ class Engine:
         self.add(packed)
         return packed
 
+    def clear(self):
+        self._ck(self._L.skb_clear(self._h), "skb_clear")
+
+    def timer_start(self):
+        self._ck(self._L.skb_timer_start(self._h), "skb_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self._L.skb_timer_stop(self._h, C.byref(ms)), "skb_timer_stop")
+        return ms.value
+
     def index(self):
         self._ck(self._L.skb_index(self._h), "skb_index")
 

@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): sketch replication and edge gather.
+
+The pair triangle shards by rows with no data-path collective (skb_triangle's part/n_parts); the
+only exchanges are (1) replicating the sketches every rank made from its share of the genomes --
+one padded NCCL all-gather per array straight out of / into the library's device buffers -- and
+(2) gathering the sparse edge lists to rank 0.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .engine import EDGE_DTYPE
+
+
+class _DevArray:
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def _dev_tensor(torch, ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevArray(ptr, n), device=device)
+
+
+def replicate_sketches(eng, dist, torch):
+    """Every rank holds the sketches of its own genomes; afterwards every rank holds all of them,
+    ordered by (rank, local order).  Collective: all ranks must call."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    device = torch.device("cuda", eng.device)
+    v = eng.sketch_view()
+    n = v.n_genomes
+    meta = {
+        "n": n, "n_seeds": v.n_seeds, "n_mkeys": v.n_marker_keys,
+        "seed_off": np.ctypeslib.as_array(v.host_seed_off, shape=(n + 1,)).copy(),
+        "total_len": np.ctypeslib.as_array(v.host_total_len, shape=(max(n, 1),))[:n].copy(),
+        "ctg_off": np.ctypeslib.as_array(v.host_ctg_off, shape=(n + 1,)).copy(),
+        "ctg_len": np.ctypeslib.as_array(v.host_ctg_len, shape=(max(int(v.n_contigs), 1),))[: int(v.n_contigs)].copy(),
+    }
+    metas = [None] * world
+    dist.all_gather_object(metas, meta)
+    gathered = []
+    for key, ptr, cnt in (("n_seeds", v.dev_seeds, v.n_seeds), ("n_mkeys", v.dev_marker_keys, v.n_marker_keys)):
+        mx = max(int(m[key]) for m in metas)
+        send = torch.zeros(max(mx, 1), dtype=torch.int64, device=device)
+        if cnt:
+            send[:cnt].copy_(_dev_tensor(torch, ptr, cnt, device))
+        recv = torch.empty(world * max(mx, 1), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(recv, send)
+        gathered.append((recv, max(mx, 1)))
+    torch.cuda.synchronize(device)
+    eng.clear()
+    (seeds, s_stride), (mkeys, m_stride) = gathered
+    for r, m in enumerate(metas):
+        if m["n"] == 0:
+            continue
+        so = np.ascontiguousarray(m["seed_off"], np.uint64)
+        tl = np.ascontiguousarray(m["total_len"], np.uint64)
+        co = np.ascontiguousarray(m["ctg_off"], np.uint32)
+        cl = np.ascontiguousarray(m["ctg_len"], np.uint32)
+        eng._ck(
+            eng._L.skb_import_sketches(
+                eng._h, int(m["n"]), C.c_void_p(seeds.data_ptr() + 8 * r * s_stride), int(m["n_seeds"]),
+                C.c_void_p(mkeys.data_ptr() + 8 * r * m_stride), int(m["n_mkeys"]), so.ctypes.data, tl.ctypes.data,
+                co.ctypes.data, cl.ctypes.data),
+            "skb_import_sketches",
+        )
+    return metas
+
+
+def gather_edges(edges, dist, torch, device=None):
+    """Variable-length edge arrays of all ranks -> one array sorted by (a, b) on rank 0 (empty elsewhere)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = torch.tensor([len(edges)], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    buf = np.zeros(mx, EDGE_DTYPE)
+    buf[: len(edges)] = edges
+    send = torch.from_numpy(buf.view(np.uint8).copy()).to(device)
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0)
+    if rank != 0:
+        return np.zeros(0, EDGE_DTYPE)
+    parts = [r.cpu().numpy().view(EDGE_DTYPE)[:c] for r, c in zip(recv, counts)]
+    out = np.concatenate(parts) if parts else np.zeros(0, EDGE_DTYPE)
+    return np.sort(out, order=["a", "b"])
+
+
+def partition_rows(n, part, n_parts):
+    """Rows of the pair triangle owned by `part` (round-robin), and how many pairs that is."""
+    rows = np.arange(part, n, n_parts)
+    return rows, int((n - 1 - rows).sum())

@@ -34,17 +34,26 @@ def _cut(g, n_contigs, rng, min_len=1000):
     return [g[a:b] for a, b in zip(cuts[:-1], cuts[1:]) if b - a >= min_len]
 
 
+def one_clade(c, per_clade, length, seed, d_lo=0.0005, d_hi=0.025, max_contigs=300, length_hi=None):
+    """Members of clade c as lists of contig byte strings.  Every clade has its own PCG64 stream
+    (seed, c), so clades can be generated in any order or in parallel."""
+    rng = np.random.Generator(np.random.PCG64([seed, c]))
+    L = length if length_hi is None else int(rng.integers(length, length_hi))
+    anc = rng.integers(0, 4, L, dtype=np.uint8)
+    out = []
+    for _ in range(per_clade):
+        d = rng.uniform(d_lo, d_hi)
+        g = _mutate(anc, d, rng)
+        nc = int(np.exp(rng.uniform(0, np.log(max_contigs))))
+        out.append([ACGT[x].tobytes() for x in _cut(g, nc, rng)])
+    return out
+
+
 def clade_genomes(n_clades, per_clade, length, seed, d_lo=0.0005, d_hi=0.025, max_contigs=300, length_hi=None):
     """Yield (clade, member, [contig byte strings]) in a fixed order."""
-    rng = np.random.Generator(np.random.PCG64(seed))
     for c in range(n_clades):
-        L = length if length_hi is None else int(rng.integers(length, length_hi))
-        anc = rng.integers(0, 4, L, dtype=np.uint8)
-        for m in range(per_clade):
-            d = rng.uniform(d_lo, d_hi)
-            g = _mutate(anc, d, rng)
-            nc = int(np.exp(rng.uniform(0, np.log(max_contigs))))
-            yield c, m, [ACGT[x].tobytes() for x in _cut(g, nc, rng)]
+        for m, contigs in enumerate(one_clade(c, per_clade, length, seed, d_lo, d_hi, max_contigs, length_hi)):
+            yield c, m, contigs
 
 
 CONFIGS = {
@@ -57,11 +66,27 @@ CONFIGS = {
 }
 
 
-def config_genomes(name, scale=1.0):
-    """Genomes of a named configuration; `scale` < 1 shrinks the number of clades (bounded samples)."""
+def config_genomes(name, n_clades=None, per_clade=None):
+    """Genomes of a named configuration; n_clades / per_clade override its shape (bounded samples)."""
     nc, per, L, Lhi, dlo, dhi, seed = CONFIGS[name]
-    nc = max(1, int(round(nc * scale)))
-    return clade_genomes(nc, per, L, seed, dlo, dhi, 300, Lhi)
+    return clade_genomes(n_clades or nc, per_clade or per, L, seed, dlo, dhi, 300, Lhi)
+
+
+def config_packed(name, pack, n_clades=None, per_clade=None, threads=None, clade_offset=0):
+    """Generate a configuration clade-parallel on host threads and pack each genome with `pack`
+    (a callable taking the list of contig byte strings).  Returns the packed genomes in fixed order."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    nc, per, L, Lhi, dlo, dhi, seed = CONFIGS[name]
+    nc, per = n_clades or nc, per_clade or per
+
+    def work(c):
+        return [pack(g) for g in one_clade(c + clade_offset, per, L, seed, dlo, dhi, 300, Lhi)]
+
+    with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:
+        res = list(ex.map(work, range(nc)))
+    return [g for clade in res for g in clade]
 
 
 def write_fasta(path, contigs, name="ctg", width=80):
