@@ -77,7 +77,8 @@ static_assert(sizeof(Cand) == 32, "cand size");
 
 // roles + chunk count per pair (one thread per pair)
 __global__ void pair_setup_kernel(DbView db, const unsigned long long *__restrict__ pairs, int64_t n_pairs,
-                                  PairInfo *__restrict__ info, uint32_t *__restrict__ nch_out) {
+                                  PairInfo *__restrict__ info, unsigned long long *__restrict__ sort_key,
+                                  uint32_t *__restrict__ idx) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const uint32_t ga = (uint32_t)(pairs[p] >> 32), gb = (uint32_t)(pairs[p] & 0xffffffffu);
@@ -89,7 +90,42 @@ __global__ void pair_setup_kernel(DbView db, const unsigned long long *__restric
     pi.r = pi.swapped ? ga : gb;
     pi.nch = db.g_chunk_off[pi.q + 1] - db.g_chunk_off[pi.q];
     info[p] = pi;
-    nch_out[p] = pi.nch;
+    sort_key[p] = ((unsigned long long)pi.r << 32) | pi.q;  // pairs sharing a reference index run together (L2 reuse)
+    idx[p] = (uint32_t)p;
+}
+
+// pairs in reference-major order: info_sorted[i] = info[perm[i]]
+__global__ void pair_gather_kernel(const PairInfo *__restrict__ info, const uint32_t *__restrict__ perm, int64_t n_pairs,
+                                   PairInfo *__restrict__ info_sorted, uint32_t *__restrict__ nch_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const PairInfo pi = info[perm[i]];
+    info_sorted[i] = pi;
+    nch_out[i] = pi.nch;
+}
+
+// ---- 16-lane segmented helpers: every lane of the warp executes them (full mask), each half gets
+// its own result.  Sub-mask REDUX would serialise the two halves and leave them diverged.
+__device__ __forceinline__ unsigned grp_max(unsigned v) {
+#pragma unroll
+    for (int d = GRP / 2; d > 0; d >>= 1) {
+        const unsigned o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t grp_min64(uint64_t v) {
+#pragma unroll
+    for (int d = GRP / 2; d > 0; d >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ int grp_sum(int v) {
+#pragma unroll
+    for (int d = GRP / 2; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
 
 __global__ void __launch_bounds__(CH_THREADS)
@@ -97,76 +133,132 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
              int64_t n_pairs, uint32_t n_tasks, Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
     __shared__ GroupSlab slabs[CH_GROUPS];
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (GRP - 1);                       // lane within group
-    const unsigned gmask = 0xffffu << (lane & GRP);        // lanes of this group
-    const int gbase = lane & GRP;                          // first lane of the group inside the warp
+    const int gl = lane & (GRP - 1);  // lane within group
     GroupSlab &w = slabs[threadIdx.x / GRP];
-    uint32_t *stage = w.bor;                               // [GRP][STAGE] (ref_pos << 1 | strand relation)
+    uint32_t *stage = w.bor;          // [GRP][STAGE] (ref_pos << 1 | strand relation)
     const uint32_t groups_total = gridDim.x * CH_GROUPS;
     const uint32_t rounds = (n_tasks + groups_total - 1) / groups_total;
 
+    // The two groups of a warp run in lockstep: loops run to the larger trip count of the two, a
+    // group without work is predicated off.  All collectives are full-mask, width-16.
     for (uint32_t round = 0; round < rounds; round++) {
         const uint32_t t = round * groups_total + blockIdx.x * CH_GROUPS + threadIdx.x / GRP;
-        __syncwarp();  // both groups of the warp start a task together
-        if (t >= n_tasks) continue;
+        bool alive = t < n_tasks;
+        __syncwarp();
         // ---- task -> (pair, chunk)
-        int64_t lo = 0, hi = n_pairs - 1;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi + 1) >> 1;
-            if (task_off[mid] <= t)
-                lo = mid;
-            else
-                hi = mid - 1;
+        uint32_t ch = 0, cstart = 0, tmask = 0;
+        int nseeds = 0, tbits = 1;
+        const uint64_t *qs = db.seeds, *T = db.tab;
+        if (alive) {
+            int64_t lo = 0, hi = n_pairs - 1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi + 1) >> 1;
+                if (task_off[mid] <= t)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const PairInfo pi = info[lo];
+            ch = t - task_off[lo];
+            const uint32_t choff = db.g_chunk_off[pi.q];
+            const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
+            const uint32_t sb = cbeg[ch];
+            nseeds = (int)(cbeg[ch + 1] - sb);
+            qs = db.seeds + db.g_seed_off[pi.q] + sb;
+            cstart = db.chunk_start[choff + ch];
+            T = db.tab + db.g_tab_off[pi.r];
+            tbits = db.g_tab_bits[pi.r];
+            tmask = (1u << tbits) - 1;
+            alive = nseeds > 0;
         }
-        const PairInfo pi = info[lo];
-        const uint32_t ch = t - task_off[lo];
-        const uint32_t choff = db.g_chunk_off[pi.q];
-        const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
-        const uint32_t sb = cbeg[ch], se = cbeg[ch + 1];
-        const int nseeds = (int)(se - sb);
-        if (nseeds <= 0) continue;
-        const uint64_t *qs = db.seeds + db.g_seed_off[pi.q] + sb;
-        const uint32_t cstart = db.chunk_start[choff + ch];
-        const uint64_t *T = db.tab + db.g_tab_off[pi.r];
-        const int tbits = db.g_tab_bits[pi.r];
-        const uint32_t tmask = (1u << tbits) - 1;
+        const int my_iters = alive ? (nseeds + GRP - 1) / GRP : 0;
+        const int w_iters = max(my_iters, __shfl_xor_sync(0xffffffffu, my_iters, GRP));
 
-        // ---- 1. anchors in query order.  Optimistic pass with the full multiplicity cap; per-level
-        //         tallies tell whether a lower cap is needed to fit MAXA (oracle: halve until it fits).
-        int mult = prm.max_mult, n = 0;
-        bool give_up = false;
-        for (int attempt = 0; attempt < 2; attempt++) {
-            int tally[4] = {0, 0, 0, 0};
-            int base = 0;
-            for (int s0 = 0; s0 < nseeds; s0 += GRP) {
-                const int s = s0 + gl;
-                int c = 0;
-                uint64_t sd = 0;
-                if (s < nseeds) {
-                    sd = qs[s];
-                    if (!seed_rep(sd)) {
-                        const uint32_t km = seed_kmer(sd);
-                        uint32_t h = tab_slot(km, tbits);
-                        for (;;) {
-                            const uint64_t e = __ldg(T + h);
-                            if (e == TAB_EMPTY) break;
-                            if (seed_kmer(e) == km) {
-                                if (c < STAGE)
-                                    stage[gl * STAGE + c] = (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
-                                c++;
-                                if (c > prm.max_mult) break;
+        // ---- 1. anchors in query order, optimistic pass with the full multiplicity cap
+        int base = 0;
+        uint64_t sd_next = (alive && gl < nseeds) ? qs[gl] : 0;
+        for (int it = 0; it < w_iters; it++) {
+            const int s = it * GRP + gl;
+            const uint64_t sd = sd_next;
+            const bool active = alive && s < nseeds;
+            sd_next = (alive && s + GRP < nseeds) ? qs[s + GRP] : 0;  // prefetch the next record
+            int c = 0;
+            if (active && !seed_rep(sd)) {
+                const uint32_t km = seed_kmer(sd);
+                uint32_t h = tab_slot(km, tbits);
+                for (;;) {
+                    const uint64_t e = __ldg(T + h);
+                    if (e == TAB_EMPTY) break;
+                    if (seed_kmer(e) == km) {
+                        if (c < STAGE)
+                            stage[gl * STAGE + c] = (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
+                        c++;
+                        if (c > prm.max_mult) break;
+                    }
+                    h = (h + 1) & tmask;
+                }
+                if (c > prm.max_mult) c = 0;
+            }
+            if (c > 1) {  // hits of one seed in ascending ref position (insertion sort, c <= 8)
+                for (int x = 1; x < c; x++) {
+                    const uint32_t v = stage[gl * STAGE + x];
+                    int y = x - 1;
+                    while (y >= 0 && stage[gl * STAGE + y] > v) {
+                        stage[gl * STAGE + y + 1] = stage[gl * STAGE + y];
+                        y--;
+                    }
+                    stage[gl * STAGE + y + 1] = v;
+                }
+            }
+            int pre = c;
+#pragma unroll
+            for (int d = 1; d < GRP; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, pre, d, GRP);
+                if (gl >= d) pre += u;
+            }
+            const int tot = __shfl_sync(0xffffffffu, pre, GRP - 1, GRP);
+            pre -= c;
+            const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
+            for (int x = 0; x < c; x++) {
+                const int dst = base + pre + x;
+                const uint32_t v = stage[gl * STAGE + x];
+                if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
+            }
+            base += tot;
+        }
+        __syncwarp();
+        int n = base;  // == group sum of tally0
+        // rare: the chunk overflows MAXA -> redo with a halved multiplicity cap until it fits (oracle rule).
+        // Slow path, per group, on the group's own mask (the two halves may diverge here).
+        if (n > MAXA) {
+            const unsigned gmask = 0xffffu << (lane & GRP);
+            int mult = prm.max_mult >> 1;
+            for (; mult >= 1; mult >>= 1) {
+                int b2 = 0;
+                for (int s0 = 0; s0 < nseeds; s0 += GRP) {
+                    const int s = s0 + gl;
+                    int c = 0;
+                    uint64_t sd = 0;
+                    if (s < nseeds) {
+                        sd = qs[s];
+                        if (!seed_rep(sd)) {
+                            const uint32_t km = seed_kmer(sd);
+                            uint32_t h = tab_slot(km, tbits);
+                            for (;;) {
+                                const uint64_t e = __ldg(T + h);
+                                if (e == TAB_EMPTY) break;
+                                if (seed_kmer(e) == km) {
+                                    if (c < STAGE)
+                                        stage[gl * STAGE + c] =
+                                            (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
+                                    c++;
+                                    if (c > mult) break;
+                                }
+                                h = (h + 1) & tmask;
                             }
-                            h = (h + 1) & tmask;
+                            if (c > mult) c = 0;
                         }
                     }
-                }
-                if (attempt == 0) {
-#pragma unroll
-                    for (int lv = 0; lv < 4; lv++)
-                        if (c >= 1 && c <= (prm.max_mult >> lv)) tally[lv] += c;
-                }
-                if (c > mult) c = 0;
-                if (c > 1) {  // hits of one seed in ascending ref position (insertion sort, c <= 8)
                     for (int x = 1; x < c; x++) {
                         const uint32_t v = stage[gl * STAGE + x];
                         int y = x - 1;
@@ -176,96 +268,72 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
                         }
                         stage[gl * STAGE + y + 1] = v;
                     }
+                    int pre = c;
+                    for (int d = 1; d < GRP; d <<= 1) {
+                        const int u = __shfl_up_sync(gmask, pre, d, GRP);
+                        if (gl >= d) pre += u;
+                    }
+                    const int tot = __shfl_sync(gmask, pre, GRP - 1, GRP);
+                    pre -= c;
+                    const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
+                    for (int x = 0; x < c; x++) {
+                        const int dst = b2 + pre + x;
+                        const uint32_t v = stage[gl * STAGE + x];
+                        if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
+                    }
+                    b2 += tot;
                 }
-                int pre = c;
-#pragma unroll
-                for (int d = 1; d < GRP; d <<= 1) {
-                    const int u = __shfl_up_sync(gmask, pre, d, GRP);
-                    if (gl >= d) pre += u;
-                }
-                const int tot = __shfl_sync(gmask, pre, GRP - 1, GRP);
-                pre -= c;
-                const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
-                for (int x = 0; x < c; x++) {
-                    const int dst = base + pre + x;
-                    const uint32_t v = stage[gl * STAGE + x];
-                    if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
-                }
-                base += tot;
+                __syncwarp(gmask);
+                n = b2;
+                if (n <= MAXA) break;
             }
-            __syncwarp(gmask);
-            if (attempt == 1) {
-                n = base;
-                break;
-            }
-#pragma unroll
-            for (int lv = 0; lv < 4; lv++) tally[lv] = (int)__reduce_add_sync(gmask, (unsigned)tally[lv]);
-            if (tally[0] <= MAXA) {
-                n = tally[0];
-                break;
-            }
-            int lv = 1;
-            while (lv < 4 && (prm.max_mult >> lv) >= 1 && tally[lv] > MAXA) lv++;
-            if (lv >= 4 || (prm.max_mult >> lv) < 1) {
-                give_up = true;
-                break;
-            }
-            mult = prm.max_mult >> lv;
+            if (n > MAXA) n = 0;  // nothing fits
         }
-        if (give_up || n < prm.min_anchors) continue;
+        __syncwarp();
+        if (n < prm.min_anchors) n = 0;
+        const int w_n = max(n, __shfl_xor_sync(0xffffffffu, n, GRP));
 
         // ---- 2. chaining DP in query order; lane gl keeps the latest anchor j with j % 16 == gl
-        uint64_t ra = 0;       // resident anchor
-        int rf = 0;            // its score
-        uint32_t rrc = 0;      // its (root << 9 | cnt)
-        for (int i = 0; i < n; i++) {
+        uint64_t ra = 0;   // resident anchor
+        int rf = 0;        // its score
+        uint32_t rrc = 0;  // its (root << 9 | cnt)
+        for (int i = 0; i < w_n; i++) {
             const uint64_t ai = w.anc[i];
             const uint32_t ri = an_r(ai), qi = an_q(ai), revi = an_rev(ai);
             const int dist = (i - 1 - gl) & (GRP - 1);  // this lane's j = i - 1 - dist
             unsigned packed = 0;
             if (dist < i) {
                 const uint32_t dq = qi - an_q(ra);
-                if (dq != 0 && dq <= (uint32_t)prm.band_bp && an_rev(ra) == revi) {
-                    const int dr = revi ? (int)an_r(ra) - (int)ri : (int)ri - (int)an_r(ra);
-                    if (dr > 0) {
-                        int gap = dr - (int)dq;
-                        gap = gap < 0 ? -gap : gap;
-                        if (gap <= prm.max_gap) {
-                            const int cand = rf + prm.anchor_score - gap;
-                            if (cand > prm.anchor_score) packed = ((unsigned)cand << 4) | (unsigned)(GRP - 1 - dist);
-                        }
-                    }
-                }
+                const int dr = revi ? (int)an_r(ra) - (int)ri : (int)ri - (int)an_r(ra);
+                int gap = dr - (int)dq;
+                gap = gap < 0 ? -gap : gap;
+                const int cand = rf + prm.anchor_score - gap;
+                if (dq != 0 && dq <= (uint32_t)prm.band_bp && an_rev(ra) == revi && dr > 0 && gap <= prm.max_gap &&
+                    cand > prm.anchor_score)
+                    packed = ((unsigned)cand << 4) | (unsigned)(GRP - 1 - dist);
             }
-            const unsigned best = __reduce_max_sync(gmask, packed);
-            int fi;
-            uint32_t rci;
-            if (best) {
-                const int bj = i - 1 - (GRP - 1 - (int)(best & (GRP - 1)));
-                const uint32_t rc = __shfl_sync(gmask, rrc, bj & (GRP - 1), GRP);
-                fi = (int)(best >> 4);
-                rci = rc + 1;  // same root, cnt + 1
-            } else {
-                fi = prm.anchor_score;
-                rci = ((uint32_t)i << 9) | 1u;
-            }
-            if (gl == (i & (GRP - 1))) {
+            const unsigned best = grp_max(packed);
+            const int bj = i - 1 - (GRP - 1 - (int)(best & (GRP - 1)));
+            const uint32_t rc = __shfl_sync(0xffffffffu, rrc, bj & (GRP - 1), GRP);
+            const int fi = best ? (int)(best >> 4) : prm.anchor_score;
+            const uint32_t rci = best ? rc + 1 : (((uint32_t)i << 9) | 1u);  // same root, cnt + 1
+            if (gl == (i & (GRP - 1)) && i < n) {
                 ra = ai;
                 rf = fi;
                 rrc = rci;
                 w.res[i] = ((uint32_t)fi << 17) | rci;
             }
         }
-        __syncwarp(gmask);
+        __syncwarp();
 
         // ---- 3. best end of every DP tree (ties: lowest index), then the chunk's top candidates
         for (int i = gl; i < n; i += GRP) w.bor[i] = 0;
-        __syncwarp(gmask);
+        __syncwarp();
         for (int i = gl; i < n; i += GRP) {
             const uint32_t x = w.res[i];
             atomicMax(&w.bor[rs_root(x)], (rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i));
         }
-        __syncwarp(gmask);
+        __syncwarp();
         uint32_t mine = 0;  // bit u <-> i = gl + 16 u
         for (int i = gl, u = 0; i < n; i += GRP, u++) {
             const uint32_t x = w.res[i];
@@ -275,6 +343,7 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
         }
         int n_out = 0;
         for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
+            if (!__any_sync(0xffffffffu, mine != 0)) break;
             uint64_t bk = ~0ull;
             int bi = -1;
             for (uint32_t mm = mine; mm; mm &= mm - 1) {
@@ -288,12 +357,9 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
                     bi = i;
                 }
             }
-            const uint32_t khi = __reduce_min_sync(gmask, (uint32_t)(bk >> 32));
-            if (khi == 0xffffffffu) break;
-            const uint32_t klo = __reduce_min_sync(gmask, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
-            const unsigned who = __ballot_sync(gmask, bk == (((uint64_t)khi << 32) | klo)) & gmask;
-            const int src = __ffs(who) - 1;  // absolute lane in warp
-            if (lane == src) {
+            const uint64_t gmin = grp_min64(bk);
+            if (gmin == ~0ull) continue;  // this group has no candidate left (the other one may)
+            if (bk == gmin) {             // keys are unique: exactly one lane of the group
                 mine &= ~(1u << ((bi - gl) / GRP));
                 const uint32_t x = w.res[bi];
                 const uint64_t ar = w.anc[rs_root(x)], ae = w.anc[bi];
@@ -306,15 +372,14 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
                 c.score = (uint16_t)rs_f(x);
                 c.n_anchors = (uint16_t)rs_cnt(x);
                 c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
-                c.ordinal = (uint8_t)rnd;
+                c.ordinal = (uint8_t)n_out;
                 c.rev = (uint8_t)an_rev(ae);
                 c.pad = 0;
-                cands[(size_t)t * SLOTS + rnd] = c;
+                cands[(size_t)t * SLOTS + n_out] = c;
             }
             n_out++;
         }
         if (gl == 0 && n_out) task_ncand[t] = (uint8_t)n_out;
-        (void)gbase;
     }
 }
 
@@ -341,7 +406,7 @@ constexpr size_t FIN_SMEM_FIXED = sizeof(Cand) * MAXP + 8 * MAXP + MAXP;
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
                 int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
-                PairOut *__restrict__ out) {
+                const uint32_t *__restrict__ perm, PairOut *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FinCtl ctl;
     Cand *cands = reinterpret_cast<Cand *>(smem);
@@ -525,7 +590,7 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
             }
             o.ani = ani > 1.0 ? 1.0 : ani;
         }
-        out[p] = o;
+        out[perm[p]] = o;
     }
 }
 

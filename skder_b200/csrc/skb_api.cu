@@ -302,9 +302,29 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     c->d_info.reserve((size_t)n_pairs, 0, c->st);
     c->d_nch.reserve((size_t)n_pairs + 1, 0, c->st);
     c->d_task_off.reserve((size_t)n_pairs + 1, 0, c->st);
-    pair_setup_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(view, d_pairs, n_pairs, c->d_info.p, c->d_nch.p);
+    PoolRef<unsigned long long> d_key(c->pool["run_ani.key"]), d_key2(c->pool["run_ani.key2"]);
+    PoolRef<uint32_t> d_idx(c->pool["run_ani.idx"]), d_perm(c->pool["run_ani.perm"]);
+    PoolRef<PairInfo> d_info_s(c->pool["run_ani.info_sorted"]);
+    d_key.reserve((size_t)n_pairs, 0, c->st);
+    d_key2.reserve((size_t)n_pairs, 0, c->st);
+    d_idx.reserve((size_t)n_pairs, 0, c->st);
+    d_perm.reserve((size_t)n_pairs, 0, c->st);
+    d_info_s.reserve((size_t)n_pairs, 0, c->st);
+    pair_setup_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(view, d_pairs, n_pairs, c->d_info.p, d_key.p,
+                                                                      d_idx.p);
     CK(cudaGetLastError());
-    c->launches++;
+    {
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_key.p, d_key2.p, d_idx.p, d_perm.p, (int64_t)n_pairs, 0, 64,
+                                           c->st));
+        c->d_tmp.reserve(bytes + 16, 0, c->st);
+        CK(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, bytes, d_key.p, d_key2.p, d_idx.p, d_perm.p, (int64_t)n_pairs, 0,
+                                           64, c->st));
+    }
+    pair_gather_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(c->d_info.p, d_perm.p, n_pairs, d_info_s.p,
+                                                                       c->d_nch.p);
+    CK(cudaGetLastError());
+    c->launches += 11;
     // batches of pairs whose tasks fit the candidate scratch (<= 8 Mi tasks = 1 GiB of slots)
     std::vector<uint32_t> h_nch((size_t)n_pairs);
     CK(cudaMemcpyAsync(h_nch.data(), c->d_nch.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->st));
@@ -327,13 +347,13 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             CK(cudaMemsetAsync(c->d_task_ncand.p, 0, (size_t)tasks, c->st));
             const unsigned want = nblk(tasks, CH_GROUPS);
             const unsigned grid = std::min<unsigned>(want, (unsigned)c->sm_count * 7u * 4u);
-            chunk_kernel<<<grid, CH_THREADS, 0, c->st>>>(view, prm, c->d_info.p + p0, c->d_task_off.p, np,
+            chunk_kernel<<<grid, CH_THREADS, 0, c->st>>>(view, prm, d_info_s.p + p0, c->d_task_off.p, np,
                                                         (uint32_t)tasks, c->d_cands.p, c->d_task_ncand.p);
             CK(cudaGetLastError());
             c->launches++;
         }
         finalize_kernel<<<(unsigned)np, FIN_THREADS, FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS, c->st>>>(
-            view, prm, c->d_info.p + p0, c->d_task_off.p, np, c->d_cands.p, c->d_task_ncand.p, d_out + p0);
+            view, prm, d_info_s.p + p0, c->d_task_off.p, np, c->d_cands.p, c->d_task_ncand.p, d_perm.p + p0, d_out);
         CK(cudaGetLastError());
         c->launches++;
         p0 = p1;
