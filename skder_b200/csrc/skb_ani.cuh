@@ -5,15 +5,17 @@
 // spans, chain count) are bit-exact against oracle/skani_oracle.c ora_pair(); ANI/AF are the same
 // IEEE double expressions (device pow() may differ from glibc's in the last ulp).
 //
-// chunk_kernel: one 16-lane group (half a warp) per task = (surviving pair, 20 kb query chunk).
-//   1. the group streams the chunk's position-ordered seeds (coalesced 8-byte records), probes the
-//      reference's hash index (L2-resident: a clade's ~50 members all hit the same tables) and lays
-//      the anchors down in QUERY order -- the order the DP wants, so there is no sort;
-//   2. chaining DP, look-back 16 == group width: lane L keeps anchor j (j = L mod 16) resident in
-//      registers, anchor i is broadcast from shared memory, every lane scores its predecessor and
-//      one REDUX (__reduce_max_sync on the group mask) picks the best (ties: nearest);
-//   3. best end of every DP tree with >= min_anchors / min_score, the chunk's top `max_chunk_chains`
-//      by (score, q0, r0) go to the task's fixed candidate slots in global memory.
+// chunk_kernel: a task = (surviving pair, 20 kb query chunk); a warp takes 32 consecutive tasks per round.
+//   P1 (warp-cooperative, one task at a time): the warp streams the chunk's position-ordered seeds
+//      (coalesced 8-byte records), probes the reference's hash index (L2-resident: a clade's members
+//      all hit the same tables) and writes the anchors in QUERY order -- the order the DP wants, so
+//      there is no sort -- to the warp's scratch slab in global memory (written once, read once:
+//      the 2*16*A term of the roofline model).
+//   P2 (thread per task): lane L runs the chaining DP of task L.  The 16-anchor look-back window
+//      lives in registers (the i-loop is unrolled 16x so every window slot is a static register);
+//      no shuffles, no shared memory, ~12 instructions per (anchor, predecessor) on 32 tasks at once.
+//   P3 (warp-cooperative): best end of every DP tree with >= min_anchors / min_score; the chunk's top
+//      `max_chunk_chains` by (score, q0, r0) go to the task's fixed candidate slots.
 // finalize_kernel: one CTA per pair gathers the candidates, orders them by (score desc, chunk,
 //   ordinal), resolves the greedy non-overlap selection in parallel rounds, accumulates per-chunk
 //   anchors/seeds and clipped spans, and reduces ANI = sum(S_c (A_c/S_c)^(1/15)) / sum(S_c),
@@ -24,16 +26,19 @@
 
 namespace skb {
 
-constexpr int GRP = 16;                       // lanes per chunk task == DP look-back
+constexpr int LB = 16;                        // DP look-back in anchors
+constexpr int DP_UNR = 2;                     // anchors per DP iteration (code size vs register moves)
+constexpr int TPW = 32;                       // tasks per warp round (one per lane in P2)
 constexpr int CH_WARPS = 4;                   // warps per CTA of the chunk kernel
 constexpr int CH_THREADS = CH_WARPS * 32;
-constexpr int CH_GROUPS = CH_THREADS / GRP;   // 8 tasks in flight per CTA
 constexpr int MAXA = 256;                     // anchors per chunk
 constexpr int MAXP = 1024;                    // chain candidates per pair
 constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
 constexpr int SLOTS = 4;                      // candidate slots per task (max_chunk_chains upper bound)
 constexpr int FIN_THREADS = 256;
 constexpr uint32_t FIN_MAX_CHUNKS = 4096;     // chunks of a query genome the finalize kernel accumulates in smem
+constexpr size_t CH_SCRATCH_ANC = (size_t)TPW * MAXA;  // uint64 per warp
+constexpr size_t CH_SCRATCH_RES = (size_t)TPW * MAXA;  // uint32 per warp
 
 struct AniParams {
     int32_t band_bp, max_gap, anchor_score, min_anchors, min_score, max_mult, max_chunk_chains;
@@ -57,13 +62,10 @@ __device__ __forceinline__ uint32_t rs_f(uint32_t x) { return x >> 17; }
 __device__ __forceinline__ uint32_t rs_root(uint32_t x) { return (x >> 9) & 0xffu; }
 __device__ __forceinline__ uint32_t rs_cnt(uint32_t x) { return x & 0x1ffu; }
 
-struct __align__(16) GroupSlab {
-    uint64_t anc[MAXA];           // anchors in (query pos, ref pos) order
-    uint32_t res[MAXA];           // DP results
-    uint32_t bor[MAXA];           // best-of-root; first GRP*STAGE words double as the hit staging area
+struct __align__(16) WarpSmem {
+    uint32_t stage[32 * STAGE];  // hits of the current 32 seeds: (ref_pos << 1 | strand relation)
+    uint32_t bor[MAXA];          // best-of-root
 };
-static_assert(sizeof(GroupSlab) == 4096, "slab size");
-static_assert(GRP * STAGE <= MAXA, "staging area must fit in bor[]");
 
 struct __align__(16) Cand {
     uint32_t q0, q1, r0, r1;
@@ -74,8 +76,9 @@ struct __align__(16) Cand {
     uint32_t pad;
 };
 static_assert(sizeof(Cand) == 32, "cand size");
+static_assert(STAGE == STAGE_CAP, "stage layout");
 
-// roles + chunk count per pair (one thread per pair)
+// roles + sort key per pair (one thread per pair)
 __global__ void pair_setup_kernel(DbView db, const unsigned long long *__restrict__ pairs, int64_t n_pairs,
                                   PairInfo *__restrict__ info, unsigned long long *__restrict__ sort_key,
                                   uint32_t *__restrict__ idx) {
@@ -104,52 +107,24 @@ __global__ void pair_gather_kernel(const PairInfo *__restrict__ info, const uint
     nch_out[i] = pi.nch;
 }
 
-// ---- 16-lane segmented helpers: every lane of the warp executes them (full mask), each half gets
-// its own result.  Sub-mask REDUX would serialise the two halves and leave them diverged.
-__device__ __forceinline__ unsigned grp_max(unsigned v) {
-#pragma unroll
-    for (int d = GRP / 2; d > 0; d >>= 1) {
-        const unsigned o = __shfl_xor_sync(0xffffffffu, v, d);
-        v = o > v ? o : v;
-    }
-    return v;
-}
-__device__ __forceinline__ uint64_t grp_min64(uint64_t v) {
-#pragma unroll
-    for (int d = GRP / 2; d > 0; d >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, v, d);
-        v = o < v ? o : v;
-    }
-    return v;
-}
-__device__ __forceinline__ int grp_sum(int v) {
-#pragma unroll
-    for (int d = GRP / 2; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-
-__global__ void __launch_bounds__(CH_THREADS)
+__global__ void __launch_bounds__(CH_THREADS, 4)
 chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-             int64_t n_pairs, uint32_t n_tasks, Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
-    __shared__ GroupSlab slabs[CH_GROUPS];
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (GRP - 1);  // lane within group
-    GroupSlab &w = slabs[threadIdx.x / GRP];
-    uint32_t *stage = w.bor;          // [GRP][STAGE] (ref_pos << 1 | strand relation)
-    const uint32_t groups_total = gridDim.x * CH_GROUPS;
-    const uint32_t rounds = (n_tasks + groups_total - 1) / groups_total;
+             int64_t n_pairs, uint32_t n_tasks, uint64_t *scratch_anc, uint32_t *scratch_res,
+             Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
+    __shared__ WarpSmem sm[CH_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &w = sm[warp];
+    const uint32_t wglobal = blockIdx.x * CH_WARPS + warp, warps_total = gridDim.x * CH_WARPS;
+    uint64_t *my_anc = scratch_anc + (size_t)wglobal * CH_SCRATCH_ANC;
+    uint32_t *my_res = scratch_res + (size_t)wglobal * CH_SCRATCH_RES;
 
-    // The two groups of a warp run in lockstep: loops run to the larger trip count of the two, a
-    // group without work is predicated off.  All collectives are full-mask, width-16.
-    for (uint32_t round = 0; round < rounds; round++) {
-        const uint32_t t = round * groups_total + blockIdx.x * CH_GROUPS + threadIdx.x / GRP;
-        bool alive = t < n_tasks;
-        __syncwarp();
-        // ---- task -> (pair, chunk)
-        uint32_t ch = 0, cstart = 0, tmask = 0;
-        int nseeds = 0, tbits = 1;
-        const uint64_t *qs = db.seeds, *T = db.tab;
-        if (alive) {
+    for (uint32_t t_base = wglobal * TPW; t_base < n_tasks; t_base += warps_total * TPW) {
+        // ---- lane L decodes task t_base + L
+        const uint32_t t = t_base + lane;
+        uint32_t ch = 0, cstart = 0, tslots = 2;
+        int nseeds = 0;
+        uint64_t seed_idx = 0, tab_idx = 0;
+        if (t < n_tasks) {
             int64_t lo = 0, hi = n_pairs - 1;
             while (lo < hi) {
                 const int64_t mid = (lo + hi + 1) >> 1;
@@ -164,222 +139,194 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
             const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
             const uint32_t sb = cbeg[ch];
             nseeds = (int)(cbeg[ch + 1] - sb);
-            qs = db.seeds + db.g_seed_off[pi.q] + sb;
+            seed_idx = db.g_seed_off[pi.q] + sb;
             cstart = db.chunk_start[choff + ch];
-            T = db.tab + db.g_tab_off[pi.r];
-            tbits = db.g_tab_bits[pi.r];
-            tmask = (1u << tbits) - 1;
-            alive = nseeds > 0;
+            tab_idx = db.g_tab_off[pi.r];
+            tslots = db.g_tab_buckets[pi.r];
         }
-        const int my_iters = alive ? (nseeds + GRP - 1) / GRP : 0;
-        const int w_iters = max(my_iters, __shfl_xor_sync(0xffffffffu, my_iters, GRP));
+        __syncwarp();
 
-        // ---- 1. anchors in query order, optimistic pass with the full multiplicity cap
-        int base = 0;
-        uint64_t sd_next = (alive && gl < nseeds) ? qs[gl] : 0;
-        for (int it = 0; it < w_iters; it++) {
-            const int s = it * GRP + gl;
-            const uint64_t sd = sd_next;
-            const bool active = alive && s < nseeds;
-            sd_next = (alive && s + GRP < nseeds) ? qs[s + GRP] : 0;  // prefetch the next record
-            int c = 0;
-            if (active && !seed_rep(sd)) {
-                const uint32_t km = seed_kmer(sd);
-                uint32_t h = tab_slot(km, tbits);
-                for (;;) {
-                    const uint64_t e = __ldg(T + h);
-                    if (e == TAB_EMPTY) break;
-                    if (seed_kmer(e) == km) {
-                        if (c < STAGE)
-                            stage[gl * STAGE + c] = (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
-                        c++;
-                        if (c > prm.max_mult) break;
-                    }
-                    h = (h + 1) & tmask;
-                }
-                if (c > prm.max_mult) c = 0;
+        // ---- P1: anchors of the 32 tasks, one task at a time, all lanes on it
+        int my_n = 0;
+        for (int k = 0; k < TPW; k++) {
+            const int ns_k = __shfl_sync(0xffffffffu, nseeds, k);
+            if (ns_k <= 0) continue;
+            const uint64_t *qs = db.seeds + __shfl_sync(0xffffffffu, seed_idx, k);
+            const uint64_t *T = db.tab + __shfl_sync(0xffffffffu, tab_idx, k);
+            const uint32_t tslots_k = __shfl_sync(0xffffffffu, tslots, k);
+            const uint32_t cstart_k = __shfl_sync(0xffffffffu, cstart, k);
+            uint64_t *anc = my_anc + (size_t)k * MAXA;
+            // optimistic pass with the full multiplicity cap; if the chunk overflows MAXA, halve the cap
+            // until it fits (oracle rule; rare)
+            int mult = prm.max_mult, n;
+            for (;;) {
+                n = emit_anchors(qs, ns_k, cstart_k, T, tslots_k, mult, prm.max_mult, MAXA, w.stage, anc, lane);
+                if (n <= MAXA || mult == 1) break;
+                mult >>= 1;
             }
-            if (c > 1) {  // hits of one seed in ascending ref position (insertion sort, c <= 8)
-                for (int x = 1; x < c; x++) {
-                    const uint32_t v = stage[gl * STAGE + x];
-                    int y = x - 1;
-                    while (y >= 0 && stage[gl * STAGE + y] > v) {
-                        stage[gl * STAGE + y + 1] = stage[gl * STAGE + y];
-                        y--;
-                    }
-                    stage[gl * STAGE + y + 1] = v;
-                }
-            }
-            int pre = c;
+            if (n > MAXA || n < prm.min_anchors) n = 0;
+            if (lane == k) my_n = n;
+        }
+        __syncwarp();  // orders the scratch writes of P1 before the reads of P2 (same warp)
+
+        // ---- P2: lane L chains task L.  The look-back window lives in registers and ROTATES:
+        //   A[UNR + d] = d-th previous anchor (d = 0 nearest); the UNR anchors of one iteration sit in
+        //   A[UNR-1 .. 0]; after the iteration everything shifts by UNR.  (A 16x unrolled static
+        //   window needs no moves but is ~50 KB of code: ncu showed 64% of stalls on instruction fetch.)
+        //   Q = q_rel + (rev << 20) + 1: other strand relation => more than band apart, no extra test;
+        //       the +1 makes (Qi - Q[j]) == dq - 1, so one unsigned compare checks 0 < dq <= band
+        //   D = R - q with R = rev ? -ref_pos : ref_pos: gap = |D_i - D_j|, d_ref = (D_i - D_j) + dq
+        //   F = f + anchor_score
+        const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
+        {
+            constexpr int UNR = DP_UNR;
+            int Q[LB + UNR], D[LB + UNR], F[LB + UNR];
+            uint32_t RC[LB + UNR];
 #pragma unroll
-            for (int d = 1; d < GRP; d <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, pre, d, GRP);
-                if (gl >= d) pre += u;
+            for (int u = 0; u < LB + UNR; u++) {
+                Q[u] = 0;
+                D[u] = 0;
+                F[u] = -(1 << 24);  // an empty slot can never win
+                RC[u] = 0;
             }
-            const int tot = __shfl_sync(0xffffffffu, pre, GRP - 1, GRP);
-            pre -= c;
-            const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
-            for (int x = 0; x < c; x++) {
-                const int dst = base + pre + x;
-                const uint32_t v = stage[gl * STAGE + x];
-                if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
-            }
-            base += tot;
-        }
-        __syncwarp();
-        int n = base;  // == group sum of tally0
-        // rare: the chunk overflows MAXA -> redo with a halved multiplicity cap until it fits (oracle rule).
-        // Slow path, per group, on the group's own mask (the two halves may diverge here).
-        if (n > MAXA) {
-            const unsigned gmask = 0xffffu << (lane & GRP);
-            int mult = prm.max_mult >> 1;
-            for (; mult >= 1; mult >>= 1) {
-                int b2 = 0;
-                for (int s0 = 0; s0 < nseeds; s0 += GRP) {
-                    const int s = s0 + gl;
-                    int c = 0;
-                    uint64_t sd = 0;
-                    if (s < nseeds) {
-                        sd = qs[s];
-                        if (!seed_rep(sd)) {
-                            const uint32_t km = seed_kmer(sd);
-                            uint32_t h = tab_slot(km, tbits);
-                            for (;;) {
-                                const uint64_t e = __ldg(T + h);
-                                if (e == TAB_EMPTY) break;
-                                if (seed_kmer(e) == km) {
-                                    if (c < STAGE)
-                                        stage[gl * STAGE + c] =
-                                            (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
-                                    c++;
-                                    if (c > mult) break;
-                                }
-                                h = (h + 1) & tmask;
-                            }
-                            if (c > mult) c = 0;
-                        }
-                    }
-                    for (int x = 1; x < c; x++) {
-                        const uint32_t v = stage[gl * STAGE + x];
-                        int y = x - 1;
-                        while (y >= 0 && stage[gl * STAGE + y] > v) {
-                            stage[gl * STAGE + y + 1] = stage[gl * STAGE + y];
-                            y--;
-                        }
-                        stage[gl * STAGE + y + 1] = v;
-                    }
-                    int pre = c;
-                    for (int d = 1; d < GRP; d <<= 1) {
-                        const int u = __shfl_up_sync(gmask, pre, d, GRP);
-                        if (gl >= d) pre += u;
-                    }
-                    const int tot = __shfl_sync(gmask, pre, GRP - 1, GRP);
-                    pre -= c;
-                    const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
-                    for (int x = 0; x < c; x++) {
-                        const int dst = b2 + pre + x;
-                        const uint32_t v = stage[gl * STAGE + x];
-                        if (dst < MAXA) w.anc[dst] = ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16);
-                    }
-                    b2 += tot;
+            const uint64_t *ap = my_anc + (size_t)lane * MAXA;
+            uint32_t *rp = my_res + (size_t)lane * MAXA;
+            const unsigned band = (unsigned)prm.band_bp;
+            for (int i0 = 0; i0 < w_n; i0 += UNR) {
+                uint64_t av[UNR];
+                if (UNR == 2) {
+                    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0));
+                    av[0] = v.x;
+                    av[UNR - 1] = v.y;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < UNR; x++) av[x] = __ldcg(ap + i0 + x);
                 }
-                __syncwarp(gmask);
-                n = b2;
-                if (n <= MAXA) break;
-            }
-            if (n > MAXA) n = 0;  // nothing fits
-        }
-        __syncwarp();
-        if (n < prm.min_anchors) n = 0;
-        const int w_n = max(n, __shfl_xor_sync(0xffffffffu, n, GRP));
-
-        // ---- 2. chaining DP in query order; lane gl keeps the latest anchor j with j % 16 == gl
-        uint64_t ra = 0;   // resident anchor
-        int rf = 0;        // its score
-        uint32_t rrc = 0;  // its (root << 9 | cnt)
-        for (int i = 0; i < w_n; i++) {
-            const uint64_t ai = w.anc[i];
-            const uint32_t ri = an_r(ai), qi = an_q(ai), revi = an_rev(ai);
-            const int dist = (i - 1 - gl) & (GRP - 1);  // this lane's j = i - 1 - dist
-            unsigned packed = 0;
-            if (dist < i) {
-                const uint32_t dq = qi - an_q(ra);
-                const int dr = revi ? (int)an_r(ra) - (int)ri : (int)ri - (int)an_r(ra);
-                int gap = dr - (int)dq;
-                gap = gap < 0 ? -gap : gap;
-                const int cand = rf + prm.anchor_score - gap;
-                if (dq != 0 && dq <= (uint32_t)prm.band_bp && an_rev(ra) == revi && dr > 0 && gap <= prm.max_gap &&
-                    cand > prm.anchor_score)
-                    packed = ((unsigned)cand << 4) | (unsigned)(GRP - 1 - dist);
-            }
-            const unsigned best = grp_max(packed);
-            const int bj = i - 1 - (GRP - 1 - (int)(best & (GRP - 1)));
-            const uint32_t rc = __shfl_sync(0xffffffffu, rrc, bj & (GRP - 1), GRP);
-            const int fi = best ? (int)(best >> 4) : prm.anchor_score;
-            const uint32_t rci = best ? rc + 1 : (((uint32_t)i << 9) | 1u);  // same root, cnt + 1
-            if (gl == (i & (GRP - 1)) && i < n) {
-                ra = ai;
-                rf = fi;
-                rrc = rci;
-                w.res[i] = ((uint32_t)fi << 17) | rci;
+                uint32_t outp[UNR];
+#pragma unroll
+                for (int x = 0; x < UNR; x++) {
+                    const uint64_t a = av[x];
+                    const int rev = (int)an_rev(a);
+                    const int qi = (int)an_q(a) + (rev << 20);
+                    const int Ri = rev ? -(int)an_r(a) : (int)an_r(a);
+                    const int Di = Ri - qi;
+                    int best = prm.anchor_score;
+                    uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
+                    const int me = UNR - 1 - x;               // this anchor's slot
+#pragma unroll
+                    for (int d = 0; d < LB; d++) {  // d = 0 is the nearest predecessor: ties keep it
+                        const int sl = me + 1 + d;
+                        const int dq1 = qi - Q[sl];  // dq - 1
+                        const int dd = Di - D[sl];
+                        const int dr1 = dd + dq1;    // d_ref - 1
+                        const int gap = dd < 0 ? -dd : dd;
+                        const int cand = F[sl] - gap;
+                        if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > best) {
+                            best = cand;
+                            brc = RC[sl];
+                        }
+                    }
+                    const uint32_t rci = brc + 1;
+                    outp[x] = ((uint32_t)best << 17) | rci;
+                    const bool live = i0 + x < my_n;
+                    Q[me] = qi + 1;
+                    D[me] = Di;
+                    F[me] = live ? best + prm.anchor_score : -(1 << 24);
+                    RC[me] = rci;
+                }
+                if (i0 < my_n) {
+                    if (UNR == 2)
+                        __stcg(reinterpret_cast<uint2 *>(rp + i0), make_uint2(outp[0], outp[UNR - 1]));
+                    else {
+#pragma unroll
+                        for (int x = 0; x < UNR; x++) __stcg(rp + i0 + x, outp[x]);
+                    }
+                }
+#pragma unroll
+                for (int u = LB + UNR - 1; u >= UNR; u--) {
+                    Q[u] = Q[u - UNR];
+                    D[u] = D[u - UNR];
+                    F[u] = F[u - UNR];
+                    RC[u] = RC[u - UNR];
+                }
             }
         }
         __syncwarp();
 
-        // ---- 3. best end of every DP tree (ties: lowest index), then the chunk's top candidates
-        for (int i = gl; i < n; i += GRP) w.bor[i] = 0;
-        __syncwarp();
-        for (int i = gl; i < n; i += GRP) {
-            const uint32_t x = w.res[i];
-            atomicMax(&w.bor[rs_root(x)], (rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i));
-        }
-        __syncwarp();
-        uint32_t mine = 0;  // bit u <-> i = gl + 16 u
-        for (int i = gl, u = 0; i < n; i += GRP, u++) {
-            const uint32_t x = w.res[i];
-            if (w.bor[rs_root(x)] == ((rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i)) && (int)rs_cnt(x) >= prm.min_anchors &&
-                (int)rs_f(x) >= prm.min_score)
-                mine |= 1u << u;
-        }
-        int n_out = 0;
-        for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
-            if (!__any_sync(0xffffffffu, mine != 0)) break;
-            uint64_t bk = ~0ull;
-            int bi = -1;
-            for (uint32_t mm = mine; mm; mm &= mm - 1) {
-                const int i = gl + GRP * (__ffs(mm) - 1);
-                const uint32_t x = w.res[i];
-                const uint64_t ar = w.anc[rs_root(x)], ae = w.anc[i];
-                const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
-                const uint64_t k = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
-                if (k < bk) {
-                    bk = k;
-                    bi = i;
+        // ---- P3: best end of every DP tree (ties: lowest index), then the chunk's top candidates
+        for (int k = 0; k < TPW; k++) {
+            const int n = __shfl_sync(0xffffffffu, my_n, k);
+            if (n == 0) continue;
+            const uint32_t ch_k = __shfl_sync(0xffffffffu, ch, k);
+            const uint32_t cstart_k = __shfl_sync(0xffffffffu, cstart, k);
+            const uint64_t *anc = my_anc + (size_t)k * MAXA;
+            const uint32_t *res = my_res + (size_t)k * MAXA;
+            uint32_t xs[MAXA / 32];
+#pragma unroll
+            for (int u = 0; u < MAXA / 32; u++) {
+                const int i = lane + 32 * u;
+                xs[u] = i < n ? __ldcg(res + i) : 0u;
+                if (i < n) w.bor[i] = 0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < MAXA / 32; u++) {
+                const int i = lane + 32 * u;
+                if (i < n) atomicMax(&w.bor[rs_root(xs[u])], (rs_f(xs[u]) << 8) | (uint32_t)(MAXA - 1 - i));
+            }
+            __syncwarp();
+            uint32_t mine = 0;  // bit u <-> i = lane + 32 u
+#pragma unroll
+            for (int u = 0; u < MAXA / 32; u++) {
+                const int i = lane + 32 * u;
+                const uint32_t x = xs[u];
+                if (i < n && w.bor[rs_root(x)] == ((rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i)) &&
+                    (int)rs_cnt(x) >= prm.min_anchors && (int)rs_f(x) >= prm.min_score)
+                    mine |= 1u << u;
+            }
+            __syncwarp();
+            int n_out = 0;
+            const uint32_t t_k = t_base + k;
+            for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
+                uint64_t bk = ~0ull;
+                int bi = -1;
+                for (uint32_t mm = mine; mm; mm &= mm - 1) {
+                    const int u = __ffs(mm) - 1, i = lane + 32 * u;
+                    const uint32_t x = __ldcg(res + i);
+                    const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + i);
+                    const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                    const uint64_t key = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
+                    if (key < bk) {
+                        bk = key;
+                        bi = i;
+                    }
                 }
+                const uint32_t khi = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32));
+                if (khi == 0xffffffffu) break;  // no candidate left
+                const uint32_t klo = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
+                if (bk == (((uint64_t)khi << 32) | klo)) {  // keys are unique: exactly one lane
+                    mine &= ~(1u << ((bi - lane) >> 5));
+                    const uint32_t x = __ldcg(res + bi);
+                    const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + bi);
+                    Cand c;
+                    c.q0 = cstart_k + an_q(ar);
+                    c.q1 = cstart_k + an_q(ae);
+                    c.r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                    c.r1 = an_r(ar) < an_r(ae) ? an_r(ae) : an_r(ar);
+                    c.chunk = ch_k;
+                    c.score = (uint16_t)rs_f(x);
+                    c.n_anchors = (uint16_t)rs_cnt(x);
+                    c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
+                    c.ordinal = (uint8_t)n_out;
+                    c.rev = (uint8_t)an_rev(ae);
+                    c.pad = 0;
+                    cands[(size_t)t_k * SLOTS + n_out] = c;
+                }
+                n_out++;
             }
-            const uint64_t gmin = grp_min64(bk);
-            if (gmin == ~0ull) continue;  // this group has no candidate left (the other one may)
-            if (bk == gmin) {             // keys are unique: exactly one lane of the group
-                mine &= ~(1u << ((bi - gl) / GRP));
-                const uint32_t x = w.res[bi];
-                const uint64_t ar = w.anc[rs_root(x)], ae = w.anc[bi];
-                Cand c;
-                c.q0 = cstart + an_q(ar);
-                c.q1 = cstart + an_q(ae);
-                c.r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
-                c.r1 = an_r(ar) < an_r(ae) ? an_r(ae) : an_r(ar);
-                c.chunk = ch;
-                c.score = (uint16_t)rs_f(x);
-                c.n_anchors = (uint16_t)rs_cnt(x);
-                c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
-                c.ordinal = (uint8_t)n_out;
-                c.rev = (uint8_t)an_rev(ae);
-                c.pad = 0;
-                cands[(size_t)t * SLOTS + n_out] = c;
-            }
-            n_out++;
+            if (lane == 0 && n_out) task_ncand[t_k] = (uint8_t)n_out;
+            __syncwarp();
         }
-        if (gl == 0 && n_out) task_ncand[t] = (uint8_t)n_out;
     }
 }
 

@@ -108,7 +108,7 @@ struct skb_ctx {
     bool indexed = false;
     int32_t n_indexed = 0;
     DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
-    DevBuf<uint8_t> d_tab_bits;
+    DevBuf<uint32_t> d_tab_buckets;
     DevBuf<uint32_t> d_chunk_begin, d_chunk_start, d_chunk_len, d_chunk_off, d_ctg_pstart, d_ctg_len, d_ctg_off,
         d_marker_cnt;
     std::vector<uint64_t> h_marker_off;    // [n+1]
@@ -131,7 +131,7 @@ struct skb_ctx {
         v.g_seed_off = d_seed_off.p;
         v.tab = d_tab.p;
         v.g_tab_off = d_tab_off.p;
-        v.g_tab_bits = d_tab_bits.p;
+        v.g_tab_buckets = d_tab_buckets.p;
         v.chunk_begin = d_chunk_begin.p;
         v.chunk_start = d_chunk_start.p;
         v.chunk_len = d_chunk_len.p;
@@ -345,10 +345,15 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             c->d_cands.reserve((size_t)tasks * SLOTS, 0, c->st);
             c->d_task_ncand.reserve((size_t)tasks, 0, c->st);
             CK(cudaMemsetAsync(c->d_task_ncand.p, 0, (size_t)tasks, c->st));
-            const unsigned want = nblk(tasks, CH_GROUPS);
-            const unsigned grid = std::min<unsigned>(want, (unsigned)c->sm_count * 7u * 4u);
+            const unsigned want = nblk(tasks, TPW * CH_WARPS);
+            const unsigned grid = std::min<unsigned>(want, (unsigned)c->sm_count * 4u);
+            PoolRef<uint64_t> d_sanc(c->pool["run_ani.scratch_anc"]);
+            PoolRef<uint32_t> d_sres(c->pool["run_ani.scratch_res"]);
+            d_sanc.reserve((size_t)grid * CH_WARPS * CH_SCRATCH_ANC, 0, c->st);
+            d_sres.reserve((size_t)grid * CH_WARPS * CH_SCRATCH_RES, 0, c->st);
             chunk_kernel<<<grid, CH_THREADS, 0, c->st>>>(view, prm, d_info_s.p + p0, c->d_task_off.p, np,
-                                                        (uint32_t)tasks, c->d_cands.p, c->d_task_ncand.p);
+                                                        (uint32_t)tasks, d_sanc.p, d_sres.p, c->d_cands.p,
+                                                        c->d_task_ncand.p);
             CK(cudaGetLastError());
             c->launches++;
         }
@@ -578,16 +583,14 @@ int skb_index(skb_ctx *ctx) {
         const uint64_t n_seeds = c->h_seed_off.back();
         // ---- host-side tables: seed hash sizes, contigs in padded coordinates, chunks
         std::vector<uint64_t> tab_off(n + 1, 0);
-        std::vector<uint8_t> tab_bits(n);
+        std::vector<uint32_t> tab_buckets(n);
         std::vector<uint32_t> ctg_pstart(c->h_ctg_len.size()), chunk_start, chunk_len;
         c->h_chunk_off.assign(n + 1, 0);
         for (int32_t g = 0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
-            int bits = 1;
-            while ((1ull << bits) < 2 * ns + 2) bits++;
-            if (bits > 31) return fail(c, SKB_ELIMIT, "genome has too many seeds");
-            tab_bits[g] = (uint8_t)bits;
-            tab_off[g + 1] = tab_off[g] + (1ull << bits);
+            if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
+            tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns / 2 + 1);  // 4 slots per bucket: load factor 0.5
+            tab_off[g + 1] = tab_off[g] + (uint64_t)tab_buckets[g] * BUCKET;
             uint32_t off = 0;
             for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
                 ctg_pstart[k] = off;
@@ -602,7 +605,7 @@ int skb_index(skb_ctx *ctx) {
         }
         c->d_seed_off.upload(c->h_seed_off, c->st);
         c->d_tab_off.upload(tab_off, c->st);
-        c->d_tab_bits.upload(tab_bits, c->st);
+        c->d_tab_buckets.upload(tab_buckets, c->st);
         c->d_total_len.upload(c->h_total_len, c->st);
         c->d_ctg_pstart.upload(ctg_pstart, c->st);
         c->d_ctg_len.upload(c->h_ctg_len, c->st);
@@ -615,10 +618,10 @@ int skb_index(skb_ctx *ctx) {
         CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
         if (n_seeds) {
             tab_insert_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n,
-                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_bits.p);
+                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_buckets.p);
             CK(cudaGetLastError());
             rep_flag_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n, c->d_tab.p,
-                                                                  c->d_tab_off.p, c->d_tab_bits.p, c->prm.max_mult);
+                                                                  c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult);
             CK(cudaGetLastError());
             c->launches += 2;
         }

@@ -43,8 +43,12 @@ __host__ __device__ inline uint64_t mm_hash64(uint64_t key) {
     return key;
 }
 
-__host__ __device__ inline uint32_t tab_slot(uint32_t kmer, int bits) {
-    return (uint32_t)(kmer * 0x9E3779B1u) >> (32 - bits);
+// Seed index layout: buckets of 4 slots (one 32-byte sector).  A k-mer's entries live in its home
+// bucket; a bucket that is full spills into the next one, so a lookup reads buckets until it meets
+// one with a free slot -- at load factor 0.5 that is 1.05 sectors on average, the same for every lane.
+constexpr uint32_t BUCKET = 4;
+__host__ __device__ inline uint32_t tab_bucket(uint32_t kmer, uint32_t n_buckets) {
+    return (uint32_t)(((uint64_t)(uint32_t)(kmer * 0x9E3779B1u) * (uint64_t)n_buckets) >> 32);
 }
 
 // Device view of the sketch DB (all pointers device memory)
@@ -54,7 +58,7 @@ struct DbView {
     const uint64_t *g_seed_off;  // [n+1]
     const uint64_t *tab;         // open-addressing seed index, all genomes
     const uint64_t *g_tab_off;   // [n+1]
-    const uint8_t *g_tab_bits;   // [n] log2(slots)
+    const uint32_t *g_tab_buckets; // [n] buckets per table (= seeds / 2 + 1), 4 slots each
     const uint32_t *chunk_begin; // genome g: n_chunks(g)+1 entries at g_chunk_off[g] + g (seed index relative to genome)
     const uint32_t *chunk_start; // [total chunks] padded coordinate of first base
     const uint32_t *chunk_len;   // [total chunks]

@@ -6,67 +6,9 @@
 // ora_screen().
 #pragma once
 #include "skb_common.cuh"
+#include "skb_probe.cuh"
 
 namespace skb {
-
-__device__ __forceinline__ int genome_of(const uint64_t *__restrict__ off, int n, uint64_t i) {
-    int lo = 0, hi = n - 1;  // last g with off[g] <= i
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (off[mid] <= i)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
-}
-
-// one thread per seed record: insert into its genome's table (linear probing, 64-bit CAS)
-__global__ void tab_insert_kernel(const uint64_t *__restrict__ seeds, uint64_t n_seeds,
-                                  const uint64_t *__restrict__ g_seed_off, int n_genomes, uint64_t *tab,
-                                  const uint64_t *__restrict__ g_tab_off, const uint8_t *__restrict__ g_tab_bits) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_seeds) return;
-    const int g = genome_of(g_seed_off, n_genomes, i);
-    const int bits = g_tab_bits[g];
-    const uint32_t mask = (1u << bits) - 1;
-    unsigned long long *T = reinterpret_cast<unsigned long long *>(tab + g_tab_off[g]);
-    const uint64_t rec = seeds[i] & ~2ull;
-    uint32_t h = tab_slot(seed_kmer(rec), bits);
-    for (;;) {
-        unsigned long long old = atomicCAS(&T[h], (unsigned long long)TAB_EMPTY, (unsigned long long)rec);
-        if (old == TAB_EMPTY) break;
-        h = (h + 1) & mask;
-    }
-}
-
-// number of table entries holding `kmer`, counting stops at `cap`
-__device__ __forceinline__ int tab_count(const uint64_t *__restrict__ T, uint32_t mask, int bits, uint32_t kmer,
-                                         int cap) {
-    uint32_t h = tab_slot(kmer, bits);
-    int c = 0;
-    for (;;) {
-        const uint64_t e = __ldg(T + h);
-        if (e == TAB_EMPTY) break;
-        if (seed_kmer(e) == kmer && ++c >= cap) break;
-        h = (h + 1) & mask;
-    }
-    return c;
-}
-
-// flag seeds whose k-mer occurs more than max_mult times in their own genome (bit 1 of the record)
-__global__ void rep_flag_kernel(uint64_t *seeds, uint64_t n_seeds, const uint64_t *__restrict__ g_seed_off,
-                                int n_genomes, const uint64_t *__restrict__ tab,
-                                const uint64_t *__restrict__ g_tab_off, const uint8_t *__restrict__ g_tab_bits,
-                                int max_mult) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_seeds) return;
-    const int g = genome_of(g_seed_off, n_genomes, i);
-    const int bits = g_tab_bits[g];
-    const uint64_t s = seeds[i];
-    const int c = tab_count(tab + g_tab_off[g], (1u << bits) - 1, bits, seed_kmer(s), max_mult + 1);
-    if (c > max_mult) seeds[i] = s | 2ull;
-}
 
 // chunk_begin: for every chunk (and one sentinel per genome) the index of its first seed
 __global__ void chunk_begin_kernel(const uint64_t *__restrict__ seeds, const uint64_t *__restrict__ g_seed_off,

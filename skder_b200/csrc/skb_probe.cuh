@@ -1,0 +1,261 @@
+// K2 -- per-reference seed index: two-choice bucketed hash table keyed by the seed k-mer, and the
+// batched anchor lookup the chunk kernel's P1 runs against it.
+//
+// Stand-in for skani's seed map (k-mer -> positions) used by the pairwise estimator behind
+// `skani triangle|dist|search` (reference call sites src/skDER/skder.py:16-18, :58-59, :119).
+//
+// Layout: buckets of 4 slots = one 32-byte sector.  A k-mer has two home buckets; an entry goes to the
+// emptier one, so at load factor 0.5 a full bucket is rare and both-full practically never happens
+// (then entries spill linearly after the first home).  A lookup therefore costs a FIXED two sector
+// reads issued together -- no dependent probe chain and no lane waiting for another lane's chain,
+// which is what bounded the linear-probing version (ncu: 37% of samples on the chain's scoreboard).
+#pragma once
+#include "skb_common.cuh"
+
+namespace skb {
+
+constexpr int PJ = 4;         // lookups in flight per lane in the batched probe
+constexpr int STAGE_CAP = 8;  // hits staged per seed (max_mult upper bound)
+
+__host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+
+__host__ __device__ inline void tab_homes(uint32_t kmer, uint32_t nb, uint32_t &b1, uint32_t &b2) {
+    b1 = mulhi32(kmer * 0x9E3779B1u, nb);
+    b2 = mulhi32((kmer ^ (kmer >> 15)) * 0x85EBCA77u + 0x165667B1u, nb);
+    if (b2 == b1) b2 = (b1 + 1 == nb) ? 0 : b1 + 1;  // nb >= 2
+}
+
+__device__ __forceinline__ int genome_of(const uint64_t *__restrict__ off, int n, uint64_t i) {
+    int lo = 0, hi = n - 1;  // last g with off[g] <= i
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+// one thread per seed record: insert into its genome's table (64-bit CAS; no deletions ever)
+__global__ void tab_insert_kernel(const uint64_t *__restrict__ seeds, uint64_t n_seeds,
+                                  const uint64_t *__restrict__ g_seed_off, int n_genomes, uint64_t *tab,
+                                  const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seeds) return;
+    const int g = genome_of(g_seed_off, n_genomes, i);
+    const uint32_t nb = g_tab_buckets[g];
+    volatile unsigned long long *T = reinterpret_cast<volatile unsigned long long *>(tab + g_tab_off[g]);
+    const unsigned long long rec = seeds[i] & ~2ull;
+    uint32_t b1, b2;
+    tab_homes(seed_kmer(rec), nb, b1, b2);
+    for (;;) {
+        int o1 = 0, o2 = 0;  // occupancy: slots fill in order
+        while (o1 < (int)BUCKET && T[(size_t)b1 * BUCKET + o1] != TAB_EMPTY) o1++;
+        while (o2 < (int)BUCKET && T[(size_t)b2 * BUCKET + o2] != TAB_EMPTY) o2++;
+        if (o1 == (int)BUCKET && o2 == (int)BUCKET) break;
+        const uint32_t tb = o2 < o1 ? b2 : b1;
+        const int slot = o2 < o1 ? o2 : o1;
+        if (atomicCAS(const_cast<unsigned long long *>(&T[(size_t)tb * BUCKET + slot]), (unsigned long long)TAB_EMPTY, rec) ==
+            TAB_EMPTY)
+            return;
+    }
+    // both homes full: spill linearly after the first home, skipping the second
+    uint32_t b = b1;
+    for (;;) {
+        b = (b + 1 == nb) ? 0 : b + 1;
+        if (b == b2) continue;
+        for (uint32_t j = 0; j < BUCKET; j++)
+            if (atomicCAS(const_cast<unsigned long long *>(&T[(size_t)b * BUCKET + j]), (unsigned long long)TAB_EMPTY, rec) ==
+                TAB_EMPTY)
+                return;
+    }
+}
+
+struct Bucket2 {
+    ulonglong2 a0, a1, c0, c1;  // home 1 slots 0..3, home 2 slots 0..3
+};
+__device__ __forceinline__ Bucket2 empty_buckets() {
+    Bucket2 B;
+    B.a0 = B.a1 = B.c0 = B.c1 = make_ulonglong2(TAB_EMPTY, TAB_EMPTY);
+    return B;
+}
+__device__ __forceinline__ Bucket2 load_buckets(const uint64_t *__restrict__ T, uint32_t b1, uint32_t b2) {
+    Bucket2 B;
+    const ulonglong2 *p1 = reinterpret_cast<const ulonglong2 *>(T + (size_t)b1 * BUCKET);
+    const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(T + (size_t)b2 * BUCKET);
+    B.a0 = __ldg(p1);
+    B.a1 = __ldg(p1 + 1);
+    B.c0 = __ldg(p2);
+    B.c1 = __ldg(p2 + 1);
+    return B;
+}
+__device__ __forceinline__ bool both_full(const Bucket2 &B) { return B.a1.y != TAB_EMPTY && B.c1.y != TAB_EMPTY; }
+
+// entries holding `kmer` (an empty slot's k-mer field, all ones, is never a canonical k-mer)
+__device__ __forceinline__ int tab_count(const uint64_t *__restrict__ T, uint32_t nb, uint32_t kmer, int cap) {
+    uint32_t b1, b2;
+    tab_homes(kmer, nb, b1, b2);
+    const Bucket2 B = load_buckets(T, b1, b2);
+    int c = (seed_kmer(B.a0.x) == kmer) + (seed_kmer(B.a0.y) == kmer) + (seed_kmer(B.a1.x) == kmer) +
+            (seed_kmer(B.a1.y) == kmer) + (seed_kmer(B.c0.x) == kmer) + (seed_kmer(B.c0.y) == kmer) +
+            (seed_kmer(B.c1.x) == kmer) + (seed_kmer(B.c1.y) == kmer);
+    if (both_full(B)) {
+        uint32_t b = b1;
+        for (;;) {
+            b = (b + 1 == nb) ? 0 : b + 1;
+            if (b == b2) continue;
+            const ulonglong2 x0 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET));
+            const ulonglong2 x1 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET) + 1);
+            c += (seed_kmer(x0.x) == kmer) + (seed_kmer(x0.y) == kmer) + (seed_kmer(x1.x) == kmer) + (seed_kmer(x1.y) == kmer);
+            if (x1.y == TAB_EMPTY || c >= cap) break;
+        }
+    }
+    return c;
+}
+
+// flag seeds whose k-mer occurs more than max_mult times in their own genome (bit 1 of the record)
+__global__ void rep_flag_kernel(uint64_t *seeds, uint64_t n_seeds, const uint64_t *__restrict__ g_seed_off,
+                                int n_genomes, const uint64_t *__restrict__ tab,
+                                const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets,
+                                int max_mult) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seeds) return;
+    const int g = genome_of(g_seed_off, n_genomes, i);
+    const uint64_t s = seeds[i];
+    const int c = tab_count(tab + g_tab_off[g], g_tab_buckets[g], seed_kmer(s), max_mult + 1);
+    if (c > max_mult) seeds[i] = s | 2ull;
+}
+
+// staged hit: (ref_pos << 1) | strand relation
+__device__ __forceinline__ uint32_t enc_hit(uint64_t e, uint64_t sd) {
+    return (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
+}
+
+// One lookup of the batch: lane's seed `sd` with its two home buckets B already loaded.  Appends the
+// seed's anchors (if it has 1..mult hits) after `base`; returns base + anchors of all 32 lanes.
+// Kept out of line: the batch calls it PJ times and the chunk kernel must stay I-cache sized.
+__device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__restrict__ T, uint32_t nb, int mult,
+                                      int max_mult, int max_anchors, uint32_t *stage, uint64_t *anc, int base, int s,
+                                      uint32_t cstart, int lane) {
+    const uint32_t km = seed_kmer(sd);
+    const uint64_t e8[8] = {B.a0.x, B.a0.y, B.a1.x, B.a1.y, B.c0.x, B.c0.y, B.c1.x, B.c1.y};
+    unsigned m = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) m |= (unsigned)(seed_kmer(e8[x]) == km) << x;
+    if (seed_rep(sd)) m = 0;  // flagged / out-of-range lanes hold all-empty buckets anyway
+    int c = __popc(m);
+    uint64_t e1 = 0;  // the hit when there is exactly one
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+        if (m & (1u << x)) e1 = e8[x];
+    const bool spilled = both_full(B);  // practically never: both homes full -> entries may have spilled
+    if (spilled || c > 1) {             // rare: repeats or spill -> stage all hits, sorted by ref position
+        int cc = 0;
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            if (m & (1u << x)) {
+                if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e8[x], sd);
+                cc++;
+            }
+        if (spilled) {
+            uint32_t b1, b2;
+            tab_homes(km, nb, b1, b2);
+            uint32_t b = b1;
+            for (;;) {
+                b = (b + 1 == nb) ? 0 : b + 1;
+                if (b == b2) continue;
+                const ulonglong2 x0 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET));
+                const ulonglong2 x1 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET) + 1);
+                const uint64_t e4[4] = {x0.x, x0.y, x1.x, x1.y};
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                    if (seed_kmer(e4[x]) == km) {
+                        if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e4[x], sd);
+                        cc++;
+                    }
+                if (x1.y == TAB_EMPTY || cc > max_mult) break;
+            }
+        }
+        c = cc;
+        if (c > mult) c = 0;
+        for (int x = 1; x < c; x++) {  // insertion sort, c <= STAGE_CAP
+            const uint32_t v = stage[lane * STAGE_CAP + x];
+            int y = x - 1;
+            while (y >= 0 && stage[lane * STAGE_CAP + y] > v) {
+                stage[lane * STAGE_CAP + y + 1] = stage[lane * STAGE_CAP + y];
+                y--;
+            }
+            stage[lane * STAGE_CAP + y + 1] = v;
+        }
+        e1 = 0;  // read back from the stage below
+    }
+    if (c > mult) c = 0;
+    int pre = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += u;
+    }
+    const int tot = __shfl_sync(0xffffffffu, pre, 31);
+    pre -= c;
+    const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
+    if (c == 1 && e1 != 0) {
+        const int dst = base + pre;
+        const uint32_t v = enc_hit(e1, sd);
+        if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+    } else {
+        for (int x = 0; x < c; x++) {
+            const int dst = base + pre + x;
+            const uint32_t v = stage[lane * STAGE_CAP + x];
+            if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+        }
+    }
+    return base + tot;
+}
+
+// P1 of one task: probe `nseeds` query seeds against table T (nb buckets); seeds with 1..mult hits
+// contribute anchors, written to anc[] in (query pos, ref pos) order as
+//   ref_pos(32) | q_rel(15) | rev(1) | seed index(16).
+// Returns the anchor count (may exceed max_anchors: then nothing past max_anchors was written).
+// Warp-cooperative, all lanes must call.  PJ x 32 seeds are looked up per batch, their 2 x PJ sector
+// reads per lane all in flight together; the next batch's seed records are prefetched meanwhile.
+__device__ __forceinline__ int emit_anchors(const uint64_t *__restrict__ qs, int nseeds, uint32_t cstart,
+                                            const uint64_t *__restrict__ T, uint32_t nb, int mult, int max_mult,
+                                            int max_anchors, uint32_t *stage, uint64_t *anc, int lane) {
+    int base = 0;
+    uint64_t sdn[PJ];
+#pragma unroll
+    for (int j = 0; j < PJ; j++) {
+        const int s = 32 * j + lane;
+        sdn[j] = s < nseeds ? qs[s] : 2ull;  // rep bit set = skip
+    }
+    for (int s0 = 0; s0 < nseeds; s0 += 32 * PJ) {
+        uint64_t sd[PJ];
+        Bucket2 B[PJ];
+#pragma unroll
+        for (int j = 0; j < PJ; j++) {
+            sd[j] = sdn[j];
+            if (!seed_rep(sd[j])) {
+                uint32_t b1, b2;
+                tab_homes(seed_kmer(sd[j]), nb, b1, b2);
+                B[j] = load_buckets(T, b1, b2);
+            } else
+                B[j] = empty_buckets();
+        }
+#pragma unroll
+        for (int j = 0; j < PJ; j++) {
+            const int s = s0 + 32 * PJ + 32 * j + lane;
+            sdn[j] = s < nseeds ? qs[s] : 2ull;
+        }
+#pragma unroll
+        for (int j = 0; j < PJ; j++) {
+            if (s0 + 32 * j >= nseeds) break;  // warp-uniform
+            base = probe_one(sd[j], B[j], T, nb, mult, max_mult, max_anchors, stage, anc, base, s0 + 32 * j + lane,
+                             cstart, lane);
+        }
+    }
+    return base;
+}
+
+}  // namespace skb
