@@ -5,17 +5,18 @@
 // spans, chain count) are bit-exact against oracle/skani_oracle.c ora_pair(); ANI/AF are the same
 // IEEE double expressions (device pow() may differ from glibc's in the last ulp).
 //
-// chunk_kernel: a task = (surviving pair, 20 kb query chunk); a warp takes 32 consecutive tasks per round.
-//   P1 (warp-cooperative, one task at a time): the warp streams the chunk's position-ordered seeds
-//      (coalesced 8-byte records), probes the reference's hash index (L2-resident: a clade's members
-//      all hit the same tables) and writes the anchors in QUERY order -- the order the DP wants, so
-//      there is no sort -- to the warp's scratch slab in global memory (written once, read once:
-//      the 2*16*A term of the roofline model).
-//   P2 (thread per task): lane L runs the chaining DP of task L.  The 16-anchor look-back window
-//      lives in registers (the i-loop is unrolled 16x so every window slot is a static register);
-//      no shuffles, no shared memory, ~12 instructions per (anchor, predecessor) on 32 tasks at once.
-//   P3 (warp-cooperative): best end of every DP tree with >= min_anchors / min_score; the chunk's top
-//      `max_chunk_chains` by (score, q0, r0) go to the task's fixed candidate slots.
+// A task = (surviving pair, 20 kb query chunk).  Three kernels, each at the occupancy its bottleneck
+// wants; anchors and DP results go through a scratch array in HBM (written once, read once: the
+// 2*16*A term of the roofline model).
+//   K4a anchor_kernel (warp per task, many warps/SM): streams the chunk's position-ordered seeds
+//      (coalesced 8-byte records), probes the reference's bucketed hash index (L2-resident: a
+//      clade's members all hit the same tables) and writes the anchors in QUERY order -- the order
+//      the DP wants, so there is no sort.
+//   K4b chain_kernel (thread per task): the chaining DP with its 16-anchor look-back window in
+//      registers; no shuffles, no shared memory, ~11 instructions per (anchor, predecessor), 32 tasks
+//      per warp instruction.
+//   K4c ends_kernel (warp per task): best end of every DP tree with >= min_anchors / min_score; the
+//      chunk's top `max_chunk_chains` by (score, q0, r0) go to the task's fixed candidate slots.
 // finalize_kernel: one CTA per pair gathers the candidates, orders them by (score desc, chunk,
 //   ordinal), resolves the greedy non-overlap selection in parallel rounds, accumulates per-chunk
 //   anchors/seeds and clipped spans, and reduces ANI = sum(S_c (A_c/S_c)^(1/15)) / sum(S_c),
@@ -28,17 +29,15 @@ namespace skb {
 
 constexpr int LB = 16;                        // DP look-back in anchors
 constexpr int DP_UNR = 2;                     // anchors per DP iteration (code size vs register moves)
-constexpr int TPW = 32;                       // tasks per warp round (one per lane in P2)
-constexpr int CH_WARPS = 4;                   // warps per CTA of the chunk kernel
-constexpr int CH_THREADS = CH_WARPS * 32;
+constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA pass
+constexpr int DP_THREADS = 128;               // K4b: one task per thread
+constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA pass
 constexpr int MAXA = 256;                     // anchors per chunk
 constexpr int MAXP = 1024;                    // chain candidates per pair
 constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
 constexpr int SLOTS = 4;                      // candidate slots per task (max_chunk_chains upper bound)
 constexpr int FIN_THREADS = 256;
 constexpr uint32_t FIN_MAX_CHUNKS = 4096;     // chunks of a query genome the finalize kernel accumulates in smem
-constexpr size_t CH_SCRATCH_ANC = (size_t)TPW * MAXA;  // uint64 per warp
-constexpr size_t CH_SCRATCH_RES = (size_t)TPW * MAXA;  // uint32 per warp
 
 struct AniParams {
     int32_t band_bp, max_gap, anchor_score, min_anchors, min_score, max_mult, max_chunk_chains;
@@ -61,11 +60,6 @@ __device__ __forceinline__ uint32_t an_sidx(uint64_t a) { return (uint32_t)a & 0
 __device__ __forceinline__ uint32_t rs_f(uint32_t x) { return x >> 17; }
 __device__ __forceinline__ uint32_t rs_root(uint32_t x) { return (x >> 9) & 0xffu; }
 __device__ __forceinline__ uint32_t rs_cnt(uint32_t x) { return x & 0x1ffu; }
-
-struct __align__(16) WarpSmem {
-    uint32_t stage[32 * STAGE];  // hits of the current 32 seeds: (ref_pos << 1 | strand relation)
-    uint32_t bor[MAXA];          // best-of-root
-};
 
 struct __align__(16) Cand {
     uint32_t q0, q1, r0, r1;
@@ -107,207 +101,218 @@ __global__ void pair_gather_kernel(const PairInfo *__restrict__ info, const uint
     nch_out[i] = pi.nch;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 4)
-chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-             int64_t n_pairs, uint32_t n_tasks, uint64_t *scratch_anc, uint32_t *scratch_res,
-             Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
-    __shared__ WarpSmem sm[CH_WARPS];
+// task descriptors: the (pair, chunk) decode is a chain of ~20 dependent loads, so it is done once,
+// one thread per task, instead of by every warp in front of its two useful loads
+struct __align__(16) TaskDesc {
+    uint64_t seed_idx;  // first seed record of the chunk (index into db.seeds)
+    uint64_t tab_idx;   // first slot of the reference's table (index into db.tab)
+    uint32_t nseeds, cstart, nb, ch;
+};
+static_assert(sizeof(TaskDesc) == 32, "desc size");
+
+__global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
+                                  int64_t n_pairs, uint32_t n_tasks, TaskDesc *__restrict__ desc) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    int64_t lo = 0, hi = n_pairs - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (task_off[mid] <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const PairInfo pi = info[lo];
+    TaskDesc d;
+    d.ch = t - task_off[lo];
+    const uint32_t choff = db.g_chunk_off[pi.q];
+    const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
+    const uint32_t sb = cbeg[d.ch];
+    d.nseeds = cbeg[d.ch + 1] - sb;
+    d.seed_idx = db.g_seed_off[pi.q] + sb;
+    d.cstart = db.chunk_start[choff + d.ch];
+    d.tab_idx = db.g_tab_off[pi.r];
+    d.nb = db.g_tab_buckets[pi.r];
+    desc[t] = d;
+}
+
+// ---- K4a: anchors.  One warp per task; the only dependent reads are descriptor -> seed records ->
+// buckets, covered by the other resident warps.
+__global__ void __launch_bounds__(ANC_THREADS, 2)
+anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint32_t n_tasks,
+              uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n) {
+    __shared__ uint32_t stage_all[ANC_THREADS / 32][32 * STAGE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem &w = sm[warp];
-    const uint32_t wglobal = blockIdx.x * CH_WARPS + warp, warps_total = gridDim.x * CH_WARPS;
-    uint64_t *my_anc = scratch_anc + (size_t)wglobal * CH_SCRATCH_ANC;
-    uint32_t *my_res = scratch_res + (size_t)wglobal * CH_SCRATCH_RES;
-
-    for (uint32_t t_base = wglobal * TPW; t_base < n_tasks; t_base += warps_total * TPW) {
-        // ---- lane L decodes task t_base + L
-        const uint32_t t = t_base + lane;
-        uint32_t ch = 0, cstart = 0, tslots = 2;
-        int nseeds = 0;
-        uint64_t seed_idx = 0, tab_idx = 0;
-        if (t < n_tasks) {
-            int64_t lo = 0, hi = n_pairs - 1;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi + 1) >> 1;
-                if (task_off[mid] <= t)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const PairInfo pi = info[lo];
-            ch = t - task_off[lo];
-            const uint32_t choff = db.g_chunk_off[pi.q];
-            const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
-            const uint32_t sb = cbeg[ch];
-            nseeds = (int)(cbeg[ch + 1] - sb);
-            seed_idx = db.g_seed_off[pi.q] + sb;
-            cstart = db.chunk_start[choff + ch];
-            tab_idx = db.g_tab_off[pi.r];
-            tslots = db.g_tab_buckets[pi.r];
-        }
-        __syncwarp();
-
-        // ---- P1: anchors of the 32 tasks, one task at a time, all lanes on it
-        int my_n = 0;
-        for (int k = 0; k < TPW; k++) {
-            const int ns_k = __shfl_sync(0xffffffffu, nseeds, k);
-            if (ns_k <= 0) continue;
-            const uint64_t *qs = db.seeds + __shfl_sync(0xffffffffu, seed_idx, k);
-            const uint64_t *T = db.tab + __shfl_sync(0xffffffffu, tab_idx, k);
-            const uint32_t tslots_k = __shfl_sync(0xffffffffu, tslots, k);
-            const uint32_t cstart_k = __shfl_sync(0xffffffffu, cstart, k);
-            uint64_t *anc = my_anc + (size_t)k * MAXA;
+    uint32_t *stage = stage_all[warp];
+    const uint32_t warps_total = gridDim.x * (ANC_THREADS / 32);
+    for (uint32_t t = blockIdx.x * (ANC_THREADS / 32) + warp; t < n_tasks; t += warps_total) {
+        const TaskDesc d = desc[t];
+        const int nseeds = (int)d.nseeds;
+        int n = 0;
+        if (nseeds > 0) {
+            const uint64_t *qs = db.seeds + d.seed_idx;
+            const uint64_t *T = db.tab + d.tab_idx;
+            uint64_t *anc = anc_all + (size_t)t * MAXA;
+            uint64_t sdn[PJ];
             // optimistic pass with the full multiplicity cap; if the chunk overflows MAXA, halve the cap
             // until it fits (oracle rule; rare)
-            int mult = prm.max_mult, n;
+            int mult = prm.max_mult;
             for (;;) {
-                n = emit_anchors(qs, ns_k, cstart_k, T, tslots_k, mult, prm.max_mult, MAXA, w.stage, anc, lane);
+                load_first_batch(qs, nseeds, lane, sdn);
+                n = emit_anchors(qs, nseeds, d.cstart, T, d.nb, mult, prm.max_mult, MAXA, stage, anc, lane, sdn, qs, 0);
                 if (n <= MAXA || mult == 1) break;
                 mult >>= 1;
             }
             if (n > MAXA || n < prm.min_anchors) n = 0;
-            if (lane == k) my_n = n;
         }
-        __syncwarp();  // orders the scratch writes of P1 before the reads of P2 (same warp)
+        if (lane == 0) task_n[t] = (uint16_t)n;
+        __syncwarp();
+    }
+}
 
-        // ---- P2: lane L chains task L.  The look-back window lives in registers and ROTATES:
-        //   A[UNR + d] = d-th previous anchor (d = 0 nearest); the UNR anchors of one iteration sit in
-        //   A[UNR-1 .. 0]; after the iteration everything shifts by UNR.  (A 16x unrolled static
-        //   window needs no moves but is ~50 KB of code: ncu showed 64% of stalls on instruction fetch.)
-        //   Q = q_rel + (rev << 20) + 1: other strand relation => more than band apart, no extra test;
-        //       the +1 makes (Qi - Q[j]) == dq - 1, so one unsigned compare checks 0 < dq <= band
-        //   D = R - q with R = rev ? -ref_pos : ref_pos: gap = |D_i - D_j|, d_ref = (D_i - D_j) + dq
-        //   F = f + anchor_score
-        const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
-        {
-            constexpr int UNR = DP_UNR;
-            int Q[LB + UNR], D[LB + UNR], F[LB + UNR];
-            uint32_t RC[LB + UNR];
+// ---- K4b: chaining DP, one THREAD per task.  The look-back window lives in registers and ROTATES:
+//   A[UNR + d] = d-th previous anchor (d = 0 nearest); the UNR anchors of one iteration sit in
+//   A[UNR-1 .. 0]; after the iteration everything shifts by UNR.  (A 16x unrolled static window needs
+//   no moves but is ~50 KB of code: ncu showed 64% of stalls on instruction fetch.)
+//   Q = q_rel + (rev << 20) + 1: other strand relation => more than band apart, no extra test;
+//       the +1 makes (Qi - Q[j]) == dq - 1, so one unsigned compare checks 0 < dq <= band
+//   D = R - q with R = rev ? -ref_pos : ref_pos: gap = |D_i - D_j|, d_ref = (D_i - D_j) + dq
+//   F = f + anchor_score
+__global__ void __launch_bounds__(DP_THREADS, 4)
+chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uint16_t *__restrict__ task_n,
+             uint32_t *__restrict__ res_all) {
+    const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
+    const int my_n = t < n_tasks ? (int)task_n[t] : 0;
+    const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
+    if (w_n == 0) return;
+    constexpr int UNR = DP_UNR;
+    static_assert(UNR == 2, "the anchor prefetch below moves 16 bytes per iteration");
+    int Q[LB + UNR], D[LB + UNR], F[LB + UNR];
+    uint32_t RC[LB + UNR];
 #pragma unroll
-            for (int u = 0; u < LB + UNR; u++) {
-                Q[u] = 0;
-                D[u] = 0;
-                F[u] = -(1 << 24);  // an empty slot can never win
-                RC[u] = 0;
-            }
-            const uint64_t *ap = my_anc + (size_t)lane * MAXA;
-            uint32_t *rp = my_res + (size_t)lane * MAXA;
-            const unsigned band = (unsigned)prm.band_bp;
-            for (int i0 = 0; i0 < w_n; i0 += UNR) {
-                uint64_t av[UNR];
-                if (UNR == 2) {
-                    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0));
-                    av[0] = v.x;
-                    av[UNR - 1] = v.y;
-                } else {
+    for (int u = 0; u < LB + UNR; u++) {
+        Q[u] = 0;
+        D[u] = 0;
+        F[u] = -(1 << 24);  // an empty slot can never win
+        RC[u] = 0;
+    }
+    const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
+    const uint64_t *ap = anc_all + (size_t)tt * MAXA;
+    uint32_t *rp = res_all + (size_t)tt * MAXA;
+    const unsigned band = (unsigned)prm.band_bp;
+    ulonglong2 vnext = __ldcg(reinterpret_cast<const ulonglong2 *>(ap));
+    for (int i0 = 0; i0 < w_n; i0 += UNR) {
+        uint64_t av[UNR];
+        av[0] = vnext.x;
+        av[1] = vnext.y;
+        if (i0 + UNR < MAXA) vnext = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR));  // next iteration's anchors
+        uint32_t outp[UNR];
 #pragma unroll
-                    for (int x = 0; x < UNR; x++) av[x] = __ldcg(ap + i0 + x);
-                }
-                uint32_t outp[UNR];
+        for (int x = 0; x < UNR; x++) {
+            const uint64_t a = av[x];
+            const int rev = (int)an_rev(a);
+            const int qi = (int)an_q(a) + (rev << 20);
+            const int Ri = rev ? -(int)an_r(a) : (int)an_r(a);
+            const int Di = Ri - qi;
+            int best = prm.anchor_score;
+            uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
+            const int me = UNR - 1 - x;               // this anchor's slot
 #pragma unroll
-                for (int x = 0; x < UNR; x++) {
-                    const uint64_t a = av[x];
-                    const int rev = (int)an_rev(a);
-                    const int qi = (int)an_q(a) + (rev << 20);
-                    const int Ri = rev ? -(int)an_r(a) : (int)an_r(a);
-                    const int Di = Ri - qi;
-                    int best = prm.anchor_score;
-                    uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
-                    const int me = UNR - 1 - x;               // this anchor's slot
-#pragma unroll
-                    for (int d = 0; d < LB; d++) {  // d = 0 is the nearest predecessor: ties keep it
-                        const int sl = me + 1 + d;
-                        const int dq1 = qi - Q[sl];  // dq - 1
-                        const int dd = Di - D[sl];
-                        const int dr1 = dd + dq1;    // d_ref - 1
-                        const int gap = dd < 0 ? -dd : dd;
-                        const int cand = F[sl] - gap;
-                        if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > best) {
-                            best = cand;
-                            brc = RC[sl];
-                        }
-                    }
-                    const uint32_t rci = brc + 1;
-                    outp[x] = ((uint32_t)best << 17) | rci;
-                    const bool live = i0 + x < my_n;
-                    Q[me] = qi + 1;
-                    D[me] = Di;
-                    F[me] = live ? best + prm.anchor_score : -(1 << 24);
-                    RC[me] = rci;
-                }
-                if (i0 < my_n) {
-                    if (UNR == 2)
-                        __stcg(reinterpret_cast<uint2 *>(rp + i0), make_uint2(outp[0], outp[UNR - 1]));
-                    else {
-#pragma unroll
-                        for (int x = 0; x < UNR; x++) __stcg(rp + i0 + x, outp[x]);
-                    }
-                }
-#pragma unroll
-                for (int u = LB + UNR - 1; u >= UNR; u--) {
-                    Q[u] = Q[u - UNR];
-                    D[u] = D[u - UNR];
-                    F[u] = F[u - UNR];
-                    RC[u] = RC[u - UNR];
+            for (int d = 0; d < LB; d++) {  // d = 0 is the nearest predecessor: ties keep it
+                const int sl = me + 1 + d;
+                const int dq1 = qi - Q[sl];  // dq - 1
+                const int dd = Di - D[sl];
+                const int dr1 = dd + dq1;    // d_ref - 1
+                const int gap = dd < 0 ? -dd : dd;
+                const int cand = F[sl] - gap;
+                if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > best) {
+                    best = cand;
+                    brc = RC[sl];
                 }
             }
+            const uint32_t rci = brc + 1;
+            outp[x] = ((uint32_t)best << 17) | rci;
+            const bool live = i0 + x < my_n;
+            Q[me] = qi + 1;
+            D[me] = Di;
+            F[me] = live ? best + prm.anchor_score : -(1 << 24);
+            RC[me] = rci;
+        }
+        if (i0 < my_n) __stcg(reinterpret_cast<uint2 *>(rp + i0), make_uint2(outp[0], outp[1]));
+#pragma unroll
+        for (int u = LB + UNR - 1; u >= UNR; u--) {
+            Q[u] = Q[u - UNR];
+            D[u] = D[u - UNR];
+            F[u] = F[u - UNR];
+            RC[u] = RC[u - UNR];
+        }
+    }
+}
+
+// ---- K4c: chain ends.  One warp per task: best end of every DP tree (ties: lowest index) with
+// >= min_anchors / min_score; the chunk's top `max_chunk_chains` by (score, q0, r0) go to the task's
+// fixed candidate slots.
+__global__ void __launch_bounds__(END_THREADS)
+ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_all, const uint32_t *__restrict__ res_all,
+            const uint16_t *__restrict__ task_n, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
+            uint8_t *__restrict__ task_ncand) {
+    __shared__ uint32_t bor_all[END_THREADS / 32][MAXA];
+    __shared__ __align__(16) uint32_t lst_all[END_THREADS / 32][SLOTS * 8 + SLOTS * 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *bor = bor_all[warp];
+    const uint32_t warps_total = gridDim.x * (END_THREADS / 32);
+    for (uint32_t t = blockIdx.x * (END_THREADS / 32) + warp; t < n_tasks; t += warps_total) {
+        const int n = task_n[t];
+        if (n == 0) continue;
+        const uint32_t ch_k = desc[t].ch, cstart_k = desc[t].cstart;
+        const uint64_t *anc = anc_all + (size_t)t * MAXA;
+        const uint32_t *res = res_all + (size_t)t * MAXA;
+        uint32_t xs[MAXA / 32];
+#pragma unroll
+        for (int u = 0; u < MAXA / 32; u++) {
+            const int i = lane + 32 * u;
+            xs[u] = i < n ? __ldcg(res + i) : 0u;
+            if (i < n) bor[i] = 0;
         }
         __syncwarp();
-
-        // ---- P3: best end of every DP tree (ties: lowest index), then the chunk's top candidates
-        for (int k = 0; k < TPW; k++) {
-            const int n = __shfl_sync(0xffffffffu, my_n, k);
-            if (n == 0) continue;
-            const uint32_t ch_k = __shfl_sync(0xffffffffu, ch, k);
-            const uint32_t cstart_k = __shfl_sync(0xffffffffu, cstart, k);
-            const uint64_t *anc = my_anc + (size_t)k * MAXA;
-            const uint32_t *res = my_res + (size_t)k * MAXA;
-            uint32_t xs[MAXA / 32];
+#pragma unroll
+        for (int u = 0; u < MAXA / 32; u++) {
+            const int i = lane + 32 * u;
+            if (i < n) atomicMax(&bor[rs_root(xs[u])], (rs_f(xs[u]) << 8) | (uint32_t)(MAXA - 1 - i));
+        }
+        __syncwarp();
+        uint32_t mine = 0;  // bit u <-> i = lane + 32 u
+#pragma unroll
+        for (int u = 0; u < MAXA / 32; u++) {
+            const int i = lane + 32 * u;
+            const uint32_t x = xs[u];
+            if (i < n && bor[rs_root(x)] == ((rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i)) &&
+                (int)rs_cnt(x) >= prm.min_anchors && (int)rs_f(x) >= prm.min_score)
+                mine |= 1u << u;
+        }
+        __syncwarp();
+        const int my_cnt = __popc(mine);
+        const int total = (int)__reduce_add_sync(0xffffffffu, (unsigned)my_cnt);
+        if (total == 0) continue;
+        if (total <= prm.max_chunk_chains) {
+            // common case: every qualifying end becomes a candidate.  All lanes fetch their ends'
+            // anchors at once, publish (candidate, key) to shared memory, then `total` lanes rank the
+            // keys for the ordinals.
+            int pre = my_cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += u;
+            }
+            pre -= my_cnt;
+            Cand *lst = reinterpret_cast<Cand *>(lst_all[warp]);                  // [SLOTS]
+            uint64_t *lkey = reinterpret_cast<uint64_t *>(lst_all[warp] + SLOTS * 8);  // [SLOTS]
 #pragma unroll
             for (int u = 0; u < MAXA / 32; u++) {
-                const int i = lane + 32 * u;
-                xs[u] = i < n ? __ldcg(res + i) : 0u;
-                if (i < n) w.bor[i] = 0;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < MAXA / 32; u++) {
-                const int i = lane + 32 * u;
-                if (i < n) atomicMax(&w.bor[rs_root(xs[u])], (rs_f(xs[u]) << 8) | (uint32_t)(MAXA - 1 - i));
-            }
-            __syncwarp();
-            uint32_t mine = 0;  // bit u <-> i = lane + 32 u
-#pragma unroll
-            for (int u = 0; u < MAXA / 32; u++) {
-                const int i = lane + 32 * u;
-                const uint32_t x = xs[u];
-                if (i < n && w.bor[rs_root(x)] == ((rs_f(x) << 8) | (uint32_t)(MAXA - 1 - i)) &&
-                    (int)rs_cnt(x) >= prm.min_anchors && (int)rs_f(x) >= prm.min_score)
-                    mine |= 1u << u;
-            }
-            __syncwarp();
-            int n_out = 0;
-            const uint32_t t_k = t_base + k;
-            for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
-                uint64_t bk = ~0ull;
-                int bi = -1;
-                for (uint32_t mm = mine; mm; mm &= mm - 1) {
-                    const int u = __ffs(mm) - 1, i = lane + 32 * u;
-                    const uint32_t x = __ldcg(res + i);
+                if ((mine >> u) & 1u) {
+                    const int i = lane + 32 * u;
+                    const uint32_t x = xs[u];
                     const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + i);
-                    const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
-                    const uint64_t key = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
-                    if (key < bk) {
-                        bk = key;
-                        bi = i;
-                    }
-                }
-                const uint32_t khi = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32));
-                if (khi == 0xffffffffu) break;  // no candidate left
-                const uint32_t klo = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
-                if (bk == (((uint64_t)khi << 32) | klo)) {  // keys are unique: exactly one lane
-                    mine &= ~(1u << ((bi - lane) >> 5));
-                    const uint32_t x = __ldcg(res + bi);
-                    const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + bi);
                     Cand c;
                     c.q0 = cstart_k + an_q(ar);
                     c.q1 = cstart_k + an_q(ae);
@@ -317,16 +322,68 @@ chunk_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const 
                     c.score = (uint16_t)rs_f(x);
                     c.n_anchors = (uint16_t)rs_cnt(x);
                     c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
-                    c.ordinal = (uint8_t)n_out;
+                    c.ordinal = 0;
                     c.rev = (uint8_t)an_rev(ae);
                     c.pad = 0;
-                    cands[(size_t)t_k * SLOTS + n_out] = c;
+                    lst[pre] = c;
+                    lkey[pre] = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)c.r0;
+                    pre++;
                 }
-                n_out++;
             }
-            if (lane == 0 && n_out) task_ncand[t_k] = (uint8_t)n_out;
             __syncwarp();
+            if (lane < total) {
+                const uint64_t key = lkey[lane];
+                int ord = 0;
+                for (int j = 0; j < total; j++) ord += lkey[j] < key;  // keys are unique
+                Cand c = lst[lane];
+                c.ordinal = (uint8_t)ord;
+                cands[(size_t)t * SLOTS + ord] = c;
+            }
+            if (lane == 0) task_ncand[t] = (uint8_t)total;
+            __syncwarp();
+            continue;
         }
+        // rare: more qualifying ends than slots -> take the best max_chunk_chains, one per round
+        int n_out = 0;
+        for (int rnd = 0; rnd < prm.max_chunk_chains; rnd++) {
+            uint64_t bk = ~0ull;
+            int bi = -1;
+            for (uint32_t mm = mine; mm; mm &= mm - 1) {
+                const int u = __ffs(mm) - 1, i = lane + 32 * u;
+                const uint32_t x = __ldcg(res + i);
+                const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + i);
+                const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                const uint64_t key = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
+                if (key < bk) {
+                    bk = key;
+                    bi = i;
+                }
+            }
+            const uint32_t khi = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32));
+            if (khi == 0xffffffffu) break;  // no candidate left
+            const uint32_t klo = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
+            if (bk == (((uint64_t)khi << 32) | klo)) {  // keys are unique: exactly one lane
+                mine &= ~(1u << ((bi - lane) >> 5));
+                const uint32_t x = __ldcg(res + bi);
+                const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + bi);
+                Cand c;
+                c.q0 = cstart_k + an_q(ar);
+                c.q1 = cstart_k + an_q(ae);
+                c.r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+                c.r1 = an_r(ar) < an_r(ae) ? an_r(ae) : an_r(ar);
+                c.chunk = ch_k;
+                c.score = (uint16_t)rs_f(x);
+                c.n_anchors = (uint16_t)rs_cnt(x);
+                c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
+                c.ordinal = (uint8_t)n_out;
+                c.rev = (uint8_t)an_rev(ae);
+                c.pad = 0;
+                cands[(size_t)t * SLOTS + n_out] = c;
+            }
+            n_out++;
+        }
+        if (lane == 0 && n_out) task_ncand[t] = (uint8_t)n_out;
+        __syncwarp();
     }
 }
 

@@ -329,7 +329,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     std::vector<uint32_t> h_nch((size_t)n_pairs);
     CK(cudaMemcpyAsync(h_nch.data(), c->d_nch.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const uint64_t max_tasks = 8ull << 20;
+    const uint64_t max_tasks = 8ull << 20;  // x 3 KiB of anchor/result scratch = 24 GiB
     int64_t p0 = 0;
     while (p0 < n_pairs) {
         uint64_t tasks = 0;
@@ -345,15 +345,27 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             c->d_cands.reserve((size_t)tasks * SLOTS, 0, c->st);
             c->d_task_ncand.reserve((size_t)tasks, 0, c->st);
             CK(cudaMemsetAsync(c->d_task_ncand.p, 0, (size_t)tasks, c->st));
-            const unsigned want = nblk(tasks, TPW * CH_WARPS);
-            const unsigned grid = std::min<unsigned>(want, (unsigned)c->sm_count * 4u);
             PoolRef<uint64_t> d_sanc(c->pool["run_ani.scratch_anc"]);
             PoolRef<uint32_t> d_sres(c->pool["run_ani.scratch_res"]);
-            d_sanc.reserve((size_t)grid * CH_WARPS * CH_SCRATCH_ANC, 0, c->st);
-            d_sres.reserve((size_t)grid * CH_WARPS * CH_SCRATCH_RES, 0, c->st);
-            chunk_kernel<<<grid, CH_THREADS, 0, c->st>>>(view, prm, d_info_s.p + p0, c->d_task_off.p, np,
-                                                        (uint32_t)tasks, d_sanc.p, d_sres.p, c->d_cands.p,
-                                                        c->d_task_ncand.p);
+            PoolRef<uint16_t> d_tn(c->pool["run_ani.task_n"]);
+            PoolRef<TaskDesc> d_desc(c->pool["run_ani.task_desc"]);
+            d_sanc.reserve((size_t)tasks * MAXA + 2, 0, c->st);
+            d_sres.reserve((size_t)tasks * MAXA, 0, c->st);
+            d_tn.reserve((size_t)tasks, 0, c->st);
+            d_desc.reserve((size_t)tasks, 0, c->st);
+            task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, d_info_s.p + p0, c->d_task_off.p, np,
+                                                                   (uint32_t)tasks, d_desc.p);
+            CK(cudaGetLastError());
+            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
+            anchor_kernel<<<g1, ANC_THREADS, 0, c->st>>>(view, prm, d_desc.p, (uint32_t)tasks, d_sanc.p, d_tn.p);
+            CK(cudaGetLastError());
+            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, (uint32_t)tasks, d_sanc.p, d_tn.p,
+                                                                         d_sres.p);
+            CK(cudaGetLastError());
+            const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
+            ends_kernel<<<g3, END_THREADS, 0, c->st>>>(prm, (uint32_t)tasks, d_sanc.p, d_sres.p, d_tn.p, d_desc.p,
+                                                      c->d_cands.p, c->d_task_ncand.p);
+            c->launches += 3;
             CK(cudaGetLastError());
             c->launches++;
         }
@@ -623,7 +635,7 @@ int skb_index(skb_ctx *ctx) {
             rep_flag_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n, c->d_tab.p,
                                                                   c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult);
             CK(cudaGetLastError());
-            c->launches += 2;
+            c->launches += 3;
         }
         const uint32_t n_entries = (uint32_t)chunk_start.size() + (uint32_t)n;
         c->d_chunk_begin.reserve(n_entries, 0, c->st);
@@ -656,7 +668,7 @@ int skb_index(skb_ctx *ctx) {
             unique_scatter_kernel<<<nblk(c->n_mkeys, 256), 256, 0, c->st>>>(d_sorted.p, c->n_mkeys, d_flag.p, d_pos.p,
                                                                            c->d_inv.p, c->d_marker_cnt.p);
             CK(cudaGetLastError());
-            c->launches += 2;
+            c->launches += 3;
             // per-genome sorted lists: swap key halves, sort again, strip ids
             c->d_markers.reserve(nu + 1, 0, c->st);
             swap_key_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_inv.p, nu, d_sorted.p);
@@ -664,7 +676,7 @@ int skb_index(skb_ctx *ctx) {
             sort_keys_u64(c, d_sorted.p, c->d_markers.p, nu);
             strip_gid_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_markers.p, nu);
             CK(cudaGetLastError());
-            c->launches += 2;
+            c->launches += 3;
             std::vector<uint32_t> cnt(n);
             CK(cudaMemcpyAsync(cnt.data(), c->d_marker_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));

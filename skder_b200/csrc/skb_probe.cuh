@@ -220,16 +220,22 @@ __device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__
 // Returns the anchor count (may exceed max_anchors: then nothing past max_anchors was written).
 // Warp-cooperative, all lanes must call.  PJ x 32 seeds are looked up per batch, their 2 x PJ sector
 // reads per lane all in flight together; the next batch's seed records are prefetched meanwhile.
-__device__ __forceinline__ int emit_anchors(const uint64_t *__restrict__ qs, int nseeds, uint32_t cstart,
-                                            const uint64_t *__restrict__ T, uint32_t nb, int mult, int max_mult,
-                                            int max_anchors, uint32_t *stage, uint64_t *anc, int lane) {
-    int base = 0;
-    uint64_t sdn[PJ];
+// first batch of a task's seed records (PJ x 32), one per lane and slot; out-of-range = flagged record
+__device__ __forceinline__ void load_first_batch(const uint64_t *__restrict__ qs, int nseeds, int lane, uint64_t (&sdn)[PJ]) {
 #pragma unroll
     for (int j = 0; j < PJ; j++) {
         const int s = 32 * j + lane;
         sdn[j] = s < nseeds ? qs[s] : 2ull;  // rep bit set = skip
     }
+}
+
+// sdn holds this task's first batch on entry and the NEXT task's first batch (qs_next/ns_next) on exit,
+// so the only latency a task exposes is that of its bucket reads.
+__device__ __forceinline__ int emit_anchors(const uint64_t *__restrict__ qs, int nseeds, uint32_t cstart,
+                                            const uint64_t *__restrict__ T, uint32_t nb, int mult, int max_mult,
+                                            int max_anchors, uint32_t *stage, uint64_t *anc, int lane,
+                                            uint64_t (&sdn)[PJ], const uint64_t *__restrict__ qs_next, int ns_next) {
+    int base = 0;
     for (int s0 = 0; s0 < nseeds; s0 += 32 * PJ) {
         uint64_t sd[PJ];
         Bucket2 B[PJ];
@@ -243,11 +249,14 @@ __device__ __forceinline__ int emit_anchors(const uint64_t *__restrict__ qs, int
             } else
                 B[j] = empty_buckets();
         }
+        if (s0 + 32 * PJ < nseeds) {
 #pragma unroll
-        for (int j = 0; j < PJ; j++) {
-            const int s = s0 + 32 * PJ + 32 * j + lane;
-            sdn[j] = s < nseeds ? qs[s] : 2ull;
-        }
+            for (int j = 0; j < PJ; j++) {
+                const int s = s0 + 32 * PJ + 32 * j + lane;
+                sdn[j] = s < nseeds ? qs[s] : 2ull;
+            }
+        } else
+            load_first_batch(qs_next, ns_next, lane, sdn);
 #pragma unroll
         for (int j = 0; j < PJ; j++) {
             if (s0 + 32 * j >= nseeds) break;  // warp-uniform
