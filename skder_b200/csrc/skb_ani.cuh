@@ -521,6 +521,7 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
     const uint32_t rcoff = db.g_ctg_off[pi.r];
     const int nrc = (int)(db.g_ctg_off[pi.r + 1] - rcoff);
     int n_acc_local = 0;
+    double l_span_q = 0, l_span_r = 0, l_a = 0, l_s = 0;  // exact in double (< 2^53); reduced below, no atomics
     for (int t = tid; t < nc; t += FIN_THREADS) {
         if (state[t] != 1) continue;
         n_acc_local++;
@@ -544,12 +545,14 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         long long b0 = (long long)c.r0 - k1 - e, b1 = (long long)c.r1 + e;
         b0 = b0 < rs ? rs : b0;
         b1 = b1 > re ? re : b1;
-        atomicAdd(&ctl.span_q, (unsigned long long)(a1 - a0 + 1));
-        atomicAdd(&ctl.span_r, (unsigned long long)(b1 - b0 + 1));
-        atomicAdd(&ctl.a_tot, (unsigned long long)c.n_anchors);
-        atomicAdd(&ctl.s_tot, (unsigned long long)c.n_seeds);
+        l_span_q += (double)(a1 - a0 + 1);
+        l_span_r += (double)(b1 - b0 + 1);
+        l_a += (double)c.n_anchors;
+        l_s += (double)c.n_seeds;
     }
-    if (n_acc_local) atomicAdd(&ctl.n_acc, n_acc_local);
+    const double t_span_q = block_sum(l_span_q, ctl.red, tid), t_span_r = block_sum(l_span_r, ctl.red, tid);
+    const double t_a = block_sum(l_a, ctl.red, tid), t_s = block_sum(l_s, ctl.red, tid);
+    const double t_acc = block_sum((double)n_acc_local, ctl.red, tid);
     __syncthreads();
     // per-chunk ANI, seed-weighted mean
     double sw = 0, sx = 0;
@@ -571,11 +574,11 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         PairOut o;
         o.ani = o.ani_raw = -1.0;
         o.af_q = o.af_r = 0.0;
-        o.n_anchors = (int64_t)ctl.a_tot;
-        o.n_seeds = (int64_t)ctl.s_tot;
-        o.span_q = (int64_t)ctl.span_q;
-        o.span_r = (int64_t)ctl.span_r;
-        o.n_chains = ctl.n_acc;
+        o.n_anchors = (int64_t)t_a;
+        o.n_seeds = (int64_t)t_s;
+        o.span_q = (int64_t)t_span_q;
+        o.span_r = (int64_t)t_span_r;
+        o.n_chains = (int)t_acc;
         o.n_chunks_used = (int)usedd;
         o.swapped = (int32_t)pi.swapped;
         o.overflow = overflow;

@@ -134,27 +134,29 @@ __device__ __forceinline__ uint32_t enc_hit(uint64_t e, uint64_t sd) {
 
 // One lookup of the batch: lane's seed `sd` with its two home buckets B already loaded.  Appends the
 // seed's anchors (if it has 1..mult hits) after `base`; returns base + anchors of all 32 lanes.
-// Kept out of line: the batch calls it PJ times and the chunk kernel must stay I-cache sized.
-__device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__restrict__ T, uint32_t nb, int mult,
-                                      int max_mult, int max_anchors, uint32_t *stage, uint64_t *anc, int base, int s,
-                                      uint32_t cstart, int lane) {
+__device__ __forceinline__ int probe_one(uint64_t sd, const Bucket2 &B, const uint64_t *__restrict__ T, uint32_t nb,
+                                         int mult, int max_mult, int max_anchors, uint32_t *stage, uint64_t *anc,
+                                         int base, int s, uint32_t cstart, int lane) {
     const uint32_t km = seed_kmer(sd);
     const uint64_t e8[8] = {B.a0.x, B.a0.y, B.a1.x, B.a1.y, B.c0.x, B.c0.y, B.c1.x, B.c1.y};
-    unsigned m = 0;
-#pragma unroll
-    for (int x = 0; x < 8; x++) m |= (unsigned)(seed_kmer(e8[x]) == km) << x;
-    if (seed_rep(sd)) m = 0;  // flagged / out-of-range lanes hold all-empty buckets anyway
-    int c = __popc(m);
+    // the k-mer is the top 30 bits of a record: compare on the high word only.  Flagged / out-of-range
+    // lanes hold all-empty buckets, whose k-mer field (all ones) is never a canonical k-mer.
+    const uint32_t kmhi = km << 2;
+    int c = 0;
     uint64_t e1 = 0;  // the hit when there is exactly one
 #pragma unroll
-    for (int x = 0; x < 8; x++)
-        if (m & (1u << x)) e1 = e8[x];
+    for (int x = 0; x < 8; x++) {
+        const bool hit = (((uint32_t)(e8[x] >> 32)) ^ kmhi) < 4u;
+        c += hit;
+        if (hit) e1 = e8[x];
+    }
     const bool spilled = both_full(B);  // practically never: both homes full -> entries may have spilled
-    if (spilled || c > 1) {             // rare: repeats or spill -> stage all hits, sorted by ref position
+    const bool slow = spilled || c > 1;
+    if (slow) {  // rare: repeats or spill -> stage all hits, sorted by ref position
         int cc = 0;
 #pragma unroll
         for (int x = 0; x < 8; x++)
-            if (m & (1u << x)) {
+            if ((((uint32_t)(e8[x] >> 32)) ^ kmhi) < 4u) {
                 if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e8[x], sd);
                 cc++;
             }
@@ -188,9 +190,18 @@ __device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__
             }
             stage[lane * STAGE_CAP + y + 1] = v;
         }
-        e1 = 0;  // read back from the stage below
     }
-    if (c > mult) c = 0;
+    const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
+    const unsigned any_slow = __ballot_sync(0xffffffffu, slow);
+    if (!any_slow) {  // common: every lane has 0 or 1 hit -> offsets from one ballot
+        const unsigned has = __ballot_sync(0xffffffffu, c == 1);
+        if (c == 1) {
+            const int dst = base + __popc(has & ((1u << lane) - 1u));
+            const uint32_t v = enc_hit(e1, sd);
+            if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+        }
+        return base + __popc(has);
+    }
     int pre = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -199,11 +210,12 @@ __device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__
     }
     const int tot = __shfl_sync(0xffffffffu, pre, 31);
     pre -= c;
-    const uint64_t lowbits = ((uint64_t)(seed_pos(sd) - cstart) << 17) | (uint64_t)s;
-    if (c == 1 && e1 != 0) {
-        const int dst = base + pre;
-        const uint32_t v = enc_hit(e1, sd);
-        if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+    if (!slow) {
+        if (c == 1) {
+            const uint32_t v = enc_hit(e1, sd);
+            if (base + pre < max_anchors)
+                __stcg(anc + base + pre, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+        }
     } else {
         for (int x = 0; x < c; x++) {
             const int dst = base + pre + x;
@@ -214,12 +226,6 @@ __device__ __noinline__ int probe_one(uint64_t sd, Bucket2 B, const uint64_t *__
     return base + tot;
 }
 
-// P1 of one task: probe `nseeds` query seeds against table T (nb buckets); seeds with 1..mult hits
-// contribute anchors, written to anc[] in (query pos, ref pos) order as
-//   ref_pos(32) | q_rel(15) | rev(1) | seed index(16).
-// Returns the anchor count (may exceed max_anchors: then nothing past max_anchors was written).
-// Warp-cooperative, all lanes must call.  PJ x 32 seeds are looked up per batch, their 2 x PJ sector
-// reads per lane all in flight together; the next batch's seed records are prefetched meanwhile.
 // first batch of a task's seed records (PJ x 32), one per lane and slot; out-of-range = flagged record
 __device__ __forceinline__ void load_first_batch(const uint64_t *__restrict__ qs, int nseeds, int lane, uint64_t (&sdn)[PJ]) {
 #pragma unroll
