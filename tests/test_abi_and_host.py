@@ -1,0 +1,133 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/skani_b200.h declares,
+the host packer agrees with the oracle's ingest, the `skani` shim parses exactly skDER's spellings and fails
+loudly (no output file) when it cannot compute.  No compute call is made: there is no GPU here."""
+import ctypes as C
+import gzip
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(built_lib):
+    from skder_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "skani_b200.h")).read()
+    declared = set(re.findall(r"\b(skb_[a-z0-9_]+)\s*\(", hdr))
+    types = {"skb_ctx", "skb_params", "skb_packed", "skb_edge", "skb_pair_detail", "skb_stats", "skb_sketch_view"}
+    declared -= types
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(L, name), name
+    # structure layouts the Python side mirrors
+    assert C.sizeof(_lib.Edge) == 32 and C.sizeof(_lib.PairDetail) == 88 and C.sizeof(_lib.Stats) == 64
+
+
+def test_no_cpu_fallback_when_gpu_missing(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from skder_b200 import engine
+
+    with pytest.raises(engine.SkbError, match="no CUDA device|no CPU path"):
+        engine.Engine(0)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "skder_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert not re.search(r"#\s*include[^\n]*oracle", src), f  # comments may cite it, code may not use it
+                assert "libskani_oracle" not in src and "oracle/_" not in src, f
+
+
+def test_packer_matches_oracle_ingest(oracle, genomes7, built_lib, tmp_path):
+    from skder_b200 import engine
+
+    for f in genomes7[:3]:
+        p, s = engine.pack_fasta(f), oracle.Sketch.from_file(f)
+        assert (p.n_bases, p.n_contigs, p.first_name) == (s.total_len, s.n_contigs, s.first_name)
+        assert np.array_equal(p.contig_lens(), s.contig_lens())
+        assert p.n_words % 2 == 0 and p.n_words * 32 >= p.n_bases
+    # plain text, CRLF, lowercase, N's, short record dropped, blank lines, junk before the first header
+    txt = b"junk\n>c1 first kept\r\nACGTNNacgt" + b"ACGT" * 200 + b"\r\n\r\n>tiny\nACGT\n>c3\n" + b"G" * 600 + b"\n"
+    plain = tmp_path / "x.fa"
+    plain.write_bytes(txt)
+    gz = tmp_path / "x.fa.gz"
+    with gzip.open(gz, "wb") as g:
+        g.write(txt)
+    for path in (plain, gz):
+        p, s = engine.pack_fasta(str(path)), oracle.Sketch.from_file(str(path))
+        assert p.n_contigs == s.n_contigs == 2 and p.n_bases == s.total_len == 810 + 600
+        assert p.first_name == s.first_name == "c1 first kept"
+        assert p.total_bases_all == 810 + 4 + 600
+    pk = engine.pack_fasta(str(plain))  # keep the owner alive: words() is a view
+    w = pk.words()
+    codes = [(int(w[j // 32]) >> (2 * (j % 32))) & 3 for j in range(10)]
+    assert codes == [0, 1, 2, 3, 0, 0, 0, 1, 2, 3]  # ACGT NN(->A) acgt
+    with pytest.raises(engine.SkbError):
+        engine.pack_fasta(str(tmp_path / "missing.fa"))
+    e = engine.pack_contigs([])
+    assert e.n_bases == 0 and e.n_contigs == 0 and e.n_words == 2
+
+
+def test_cli_parses_exactly_skders_spellings():
+    from skder_b200 import cli
+
+    sub, o = cli.parse_args("triangle -l L.txt --min-af 50.0 -E -s 89.5 -t 4 -o out.tsv".split())
+    assert sub == "triangle" and (o["list"], o["min_af"], o["screen"], o["threads"], o["out"]) == ("L.txt", 50.0, 89.5, 4, "out.tsv")
+    sub, o = cli.parse_args("sketch -l L.txt -o db -t 8".split())
+    assert sub == "sketch" and o["out"] == "db"
+    sub, o = cli.parse_args("search q.fa -d db -o r.tsv -t 2".split())
+    assert sub == "search" and o["positional"] == ["q.fa"] and o["screen"] == 80.0 and o["min_af"] == 15.0
+    sub, o = cli.parse_args("dist --rl R --ql Q -s 85 -o Skani_Dist_Output.txt".split())
+    assert sub == "dist" and o["screen"] == 85.0
+    sub, o = cli.parse_args(["dist", "--rl", "R", "--ql", "Q", "", "-t", "3", "-o", "x"])  # empty -p splice
+    assert o["threads"] == 3
+    for bad in ("triangle -l L -o o", "triangle -l L -E -o o --fast", "triangle -l L -E -o o -c 30", "dist --rl R -o o",
+                "search -d db -o o", "frobnicate", "triangle -l L -E -o o --no-learned-ani", "triangle -l L -E -o o -s x"):
+        with pytest.raises(cli.UsageError):
+            cli.parse_args(bad.split())
+
+
+def test_cli_rows_and_loud_failure(tmp_path):
+    from skder_b200 import cli
+    from skder_b200.engine import EDGE_DTYPE
+
+    e = np.zeros(2, EDGE_DTYPE)
+    e[0] = (0, 2, 98.785, 95.456, 92.934)
+    e[1] = (1, 2, 100.0, 99.995, 50.0)
+    rows = cli.triangle_rows(["/a", "/b", "/c"], ["na", "nb", "nc"], e)
+    assert rows[0] == "/a\t/c\t98.78\t95.46\t92.93\tna\tnc\n" or rows[0] == "/a\t/c\t98.79\t95.46\t92.93\tna\tnc\n"
+    assert rows[1].split("\t")[2:5] == ["100.00", "100.00" if "%.2f" % 99.995 == "100.00" else "99.99", "50.00"]
+    r = cli.rect_rows(["/r1", "/r2", "/q"], ["n1", "n2", "nq"], np.array([(0, 2, 97.0, 80.0, 81.0), (1, 2, 99.0, 90.0, 91.0)], EDGE_DTYPE))
+    assert [x.split("\t")[0] for x in r] == ["/r2", "/r1"]  # grouped by query, ANI descending
+    assert cli.HEADER == open(os.path.join(ROOT, "tests", "golden", "skder_results", "Skani_Triangle_Edge_Output.txt")).readline()
+    # unsupported flag or missing GPU: non-zero exit, NO output file (skDER's runCmd checks only that), a log beside it
+    lst = tmp_path / "l.txt"
+    lst.write_text("/nonexistent/genome.fa\n")
+    out = tmp_path / "edges.tsv"
+    shim = os.path.join(ROOT, "skder_b200", "bin", "skani")
+    for argv in (["triangle", "-l", str(lst), "-E", "--slow", "-o", str(out)], ["triangle", "-l", str(lst), "-E", "-o", str(out)]):
+        rc = subprocess.call([sys.executable, shim] + argv, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert rc != 0 and not out.exists()
+    assert os.path.exists(str(out) + ".skani_b200.log")
+
+
+def test_synthetic_generator_is_deterministic():
+    from skder_b200 import synth
+
+    a = synth.one_clade(3, 2, 60_000, 11)
+    b = synth.one_clade(3, 2, 60_000, 11)
+    assert a == b and a != synth.one_clade(4, 2, 60_000, 11)
+    g = list(synth.config_genomes("tiny"))
+    assert len(g) == 12 and all(sum(map(len, c)) > 20_000 for _, _, c in g)
