@@ -122,6 +122,8 @@ typedef struct {
     int64_t launches;         /* kernels launched by this call */
     int64_t sum_query_seeds;  /* sum over screened pairs of the query genome's seed count (roofline bytes) */
     int64_t sum_anchors;      /* sum over screened pairs of chained anchors (roofline bytes) */
+    float ms_anchor;          /* device time of the anchor kernel (dominant kernel), summed over its launches */
+    int32_t n_anchor_launches;
 } skb_stats;
 
 /* `skani triangle -l list --min-af A -E -s S` (skder.py:16-18): all pairs a<b of the DB whose

@@ -78,6 +78,8 @@ class Stats(C.Structure):
         ("launches", C.c_int64),
         ("sum_query_seeds", C.c_int64),
         ("sum_anchors", C.c_int64),
+        ("ms_anchor", C.c_float),
+        ("n_anchor_launches", C.c_int32),
     ]
 
 

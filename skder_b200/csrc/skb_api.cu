@@ -94,6 +94,10 @@ struct skb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     bool ani_attr_set = false;
+    std::vector<cudaEvent_t> anchor_ev;  // start/stop pairs around the anchor kernel launches of the current call
+    int anchor_ev_used = 0;
+    float last_ms_anchor = 0;
+    int last_anchor_launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
 
     // ---- sketch DB (host metadata)
@@ -290,6 +294,7 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
 //   task_off  : exclusive prefix of chunk counts -> task id = (pair, chunk)
 //   cands     : SLOTS candidate slots per task;  task_ncand: how many are filled
 void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, PairOut *d_out) {
+    c->anchor_ev_used = 0;
     if (n_pairs == 0) return;
     if (n_pairs >= (1ll << 31)) throw CudaFail{"too many surviving pairs in one call"};
     if (!c->ani_attr_set) {
@@ -357,8 +362,18 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                                                                    (uint32_t)tasks, d_desc.p);
             CK(cudaGetLastError());
             const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
+            if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
+                cudaEvent_t a, b;
+                CK(cudaEventCreate(&a));
+                CK(cudaEventCreate(&b));
+                c->anchor_ev.push_back(a);
+                c->anchor_ev.push_back(b);
+            }
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st));
             anchor_kernel<<<g1, ANC_THREADS, 0, c->st>>>(view, prm, d_desc.p, (uint32_t)tasks, d_sanc.p, d_tn.p);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st));
+            c->anchor_ev_used += 2;
             chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, (uint32_t)tasks, d_sanc.p, d_tn.p,
                                                                          d_sres.p);
             CK(cudaGetLastError());
@@ -416,6 +431,14 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
     ne = h3[0];
     run.sums[0] = h3[1];
     run.sums[1] = h3[2];
+    c->last_ms_anchor = 0;
+    c->last_anchor_launches = c->anchor_ev_used / 2;
+    for (int i = 0; i + 1 < c->anchor_ev_used; i += 2) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->anchor_ev[i], c->anchor_ev[i + 1]));
+        c->last_ms_anchor += ms;
+    }
+    c->anchor_ev_used = 0;
     run.edges.resize((size_t)ne);
     if (ne) CK(cudaMemcpy(run.edges.data(), d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost));
     std::sort(run.edges.begin(), run.edges.end(), [](const skb_edge &x, const skb_edge &y) {
@@ -506,6 +529,7 @@ int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
 void skb_destroy(skb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (cudaEvent_t e : ctx->anchor_ev) cudaEventDestroy(e);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->st) {
@@ -793,6 +817,8 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
             stats->ms_screen = ms01;
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;
+            stats->ms_anchor = c->last_ms_anchor;
+            stats->n_anchor_launches = c->last_anchor_launches;
             stats->launches = c->launches - launches0;
             stats->sum_query_seeds = (int64_t)run.sums[0];
             stats->sum_anchors = (int64_t)run.sums[1];
@@ -885,6 +911,8 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
             stats->ms_screen = ms01;
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;
+            stats->ms_anchor = c->last_ms_anchor;
+            stats->n_anchor_launches = c->last_anchor_launches;
             stats->launches = c->launches - launches0;
             stats->sum_query_seeds = (int64_t)run.sums[0];
             stats->sum_anchors = (int64_t)run.sums[1];

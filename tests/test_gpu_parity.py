@@ -158,3 +158,80 @@ def test_synthetic_clades(oracle, built_lib):
         assert got == want
         # 3 clades x 4: only within-clade pairs survive
         assert len(want) == 3 * 6
+
+
+def _run_shim(argv):
+    import subprocess
+    import sys
+
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "skder_b200", "bin", "skani")
+    return subprocess.call([sys.executable, shim] + argv, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def test_skani_shim_triangle_dist_search_bytes_equal_oracle(genomes7, oracle, built_lib, tmp_path):
+    """The `skani` stand-in, invoked exactly as skDER spells it (reference src/skDER/skder.py:16-18, 58-59, 103, 119),
+    writes byte-for-byte the TSV the CPU oracle writes."""
+    from oracle import skani_cpu
+
+    lst = tmp_path / "All_Genomes_Listing.txt"
+    lst.write_text("".join(p + "\n" for p in reversed(genomes7)))  # list order must not matter
+    out = tmp_path / "Skani_Triangle_Edge_Output.txt"
+    assert _run_shim(["triangle", "-l", str(lst), "--min-af", "50.0", "-E", "-s", "89.0", "-t", "4", "-o", str(out)]) == 0
+    assert out.read_text() == skani_cpu.triangle_tsv(genomes7, 89.0, 50.0, threads=4)
+    # dist: reps vs non-reps, no -t, default screen / min-af
+    rl, ql = tmp_path / "Reps_Listing.txt", tmp_path / "NonReps_Listing.txt"
+    rl.write_text("".join(p + "\n" for p in genomes7[:4]))
+    ql.write_text("".join(p + "\n" for p in genomes7[4:]))
+    dout = tmp_path / "Skani_Dist_Output.txt"
+    assert _run_shim(["dist", "--rl", str(rl), "--ql", str(ql), "-s", "89.0", "-o", str(dout)]) == 0
+    assert dout.read_text() == skani_cpu.rect_tsv(genomes7[:4], genomes7[4:], 89.0, 15.0, threads=4)
+    # sketch + search (low_mem_greedy): DB directory, then one query against it
+    db = tmp_path / "skani_sketch_all.db"
+    assert _run_shim(["sketch", "-l", str(lst), "-o", str(db), "-t", "4"]) == 0 and db.is_dir()
+    sout = tmp_path / "current_search_results.tsv"
+    q = genomes7[2]
+    assert _run_shim(["search", q, "-d", str(db), "-o", str(sout), "-t", "4"]) == 0
+    rows = [ln.split("\t") for ln in sout.read_text().splitlines()[1:]]
+    assert len(rows) == 7 and all(r[1] == q for r in rows)  # 6 partners + the genome's own copy in the DB
+    self_row = [r for r in rows if r[0] == q][0]
+    assert self_row[2] == "100.00" and float(self_row[3]) > 99.5
+    sk = {p: oracle.Sketch.from_file(p) for p in genomes7}
+    for r in rows:
+        res = oracle.pair(sk[r[0]], sk[q]) if r[0] != q else None
+        if res is not None:
+            assert (r[2], r[3], r[4]) == ("%.2f" % (res.ani * 100), "%.2f" % (res.af_a * 100), "%.2f" % (res.af_b * 100))
+    assert [float(r[2]) for r in rows] == sorted((float(r[2]) for r in rows), reverse=True)  # ANI descending
+    # unsupported option: non-zero exit and the previous output is not replaced by a partial file
+    bad = tmp_path / "bad.tsv"
+    assert _run_shim(["triangle", "-l", str(lst), "-E", "--medium", "-o", str(bad)]) != 0 and not bad.exists()
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE config-sized genomes (5 Mbp): size-independent properties through the C-ABI."""
+    from skder_b200 import engine, synth
+
+    gens = [engine.pack_contigs(c) for c in synth.one_clade(0, 6, 5_000_000, 99)] + \
+           [engine.pack_contigs(c) for c in synth.one_clade(1, 2, 5_000_000, 99)]
+    with engine.Engine(0) as e:
+        e.add(gens)
+        e.add([gens[0]])  # an exact copy of genome 0 becomes genome 8
+        e.index()
+        edges, st = e.triangle(screen=80.0, min_af=15.0)
+        got = {(int(x["a"]), int(x["b"])): x for x in edges}
+        # within-clade pairs only; cross-clade pairs die in the prescreen
+        clade = lambda g: 0 if g < 6 or g == 8 else 1
+        assert all(clade(a) == clade(b) for a, b in got) and len(got) == 21 + 1
+        assert st.n_pairs_total == 36 and st.n_pairs_screened == 22
+        # idempotence: a genome against its copy is 100 / ~100 / ~100
+        x = got[(0, 8)]
+        assert x["ani"] == 100.0 and x["af_a"] > 99.5 and x["af_b"] > 99.5  # chain ends are clipped to chunk bounds
+        # the copy behaves exactly like the original against everyone else
+        for b in range(1, 6):
+            assert (got[(0, b)]["ani"], got[(0, b)]["af_a"]) == (got[(b, 8)]["ani"], got[(b, 8)]["af_b"])
+        # ANI decreases with the mutation rates that generated the clade (d_i + d_j), within sampling noise
+        d = e.pairs_detail([0, 0], [1, 2])
+        assert all(0.90 < x.ani_raw < 1.0 and x.overflow == 0 for x in d)
+        # sketch density at full size
+        for g in range(8):
+            s = e.sizes(g)
+            assert abs(s["n_seeds"] / (s["total_len"] / 125.0) - 1) < 0.03
