@@ -320,7 +320,7 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "anchor_kernel_traffic.json")))
-        if tj.get("workload") == args.workload:
+        if tj.get("workload") == args.workload and world == 1:
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass

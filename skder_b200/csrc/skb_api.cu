@@ -88,7 +88,8 @@ inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t
 
 struct skb_ctx {
     int device = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::vector<cudaEvent_t> up_ev;
     skb_params prm;
     std::string err;
     int64_t launches = 0;
@@ -211,7 +212,8 @@ void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int 
 }
 
 // ---- sketch a batch of packed genomes [g0, g1) of the caller's list ------------------------------
-void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1) {
+void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1, const uint64_t *d_words,
+                  cudaEvent_t uploaded) {
     const int32_t nb = g1 - g0;
     std::vector<uint64_t> word_off(nb + 1, 0), nbases(nb), ctg_start;
     std::vector<uint32_t> ctg_off(nb + 1, 0), tile_off(nb + 1, 0);
@@ -230,12 +232,9 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     }
     const uint32_t n_tiles = tile_off[nb];
     const size_t n_warps = (size_t)n_tiles * SK_WARPS;
-    PoolRef<uint64_t> d_packed(c->pool["sketch_batch.d_packed"]), d_word_off(c->pool["sketch_batch.d_word_off"]), d_nbases(c->pool["sketch_batch.d_nbases"]), d_ctg_start(c->pool["sketch_batch.d_ctg_start"]);
+    PoolRef<uint64_t> d_word_off(c->pool["sketch_batch.d_word_off"]), d_nbases(c->pool["sketch_batch.d_nbases"]), d_ctg_start(c->pool["sketch_batch.d_ctg_start"]);
     PoolRef<uint32_t> d_ctg_off(c->pool["sketch_batch.d_ctg_off"]), d_tile_off(c->pool["sketch_batch.d_tile_off"]), d_cnt_s(c->pool["sketch_batch.d_cnt_s"]), d_cnt_m(c->pool["sketch_batch.d_cnt_m"]), d_off_s(c->pool["sketch_batch.d_off_s"]), d_off_m(c->pool["sketch_batch.d_off_m"]);
-    d_packed.reserve(word_off[nb] + 2, 0, c->st);
-    for (int32_t i = 0; i < nb; i++)
-        CK(cudaMemcpyAsync(d_packed.p + word_off[i], gen[g0 + i]->words, (size_t)gen[g0 + i]->n_words * 8,
-                           cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamWaitEvent(c->st, uploaded, 0));  // the batch's words were enqueued on the copy stream
     d_word_off.upload(word_off, c->st);
     d_nbases.upload(nbases, c->st);
     d_ctg_start.upload(ctg_start, c->st);
@@ -248,7 +247,7 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     CK(cudaMemsetAsync(d_cnt_s.p + n_warps, 0, 4, c->st));
     CK(cudaMemsetAsync(d_cnt_m.p + n_warps, 0, 4, c->st));
     SketchBatch b;
-    b.packed = d_packed.p;
+    b.packed = d_words;
     b.g_word_off = d_word_off.p;
     b.g_nbases = d_nbases.p;
     b.g_ctg_off = d_ctg_off.p;
@@ -256,7 +255,10 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     b.tile_off = d_tile_off.p;
     b.n = nb;
     b.first_gid = (uint32_t)c->n();
-    sketch_kernel<false><<<n_tiles, SK_THREADS, 0, c->st>>>(b, d_cnt_s.p, d_cnt_m.p, nullptr, nullptr, nullptr, nullptr);
+    PoolRef<ulonglong2> d_masks(c->pool["sketch_batch.d_masks"]);
+    d_masks.reserve(n_warps * 32, 0, c->st);
+    sketch_kernel<false><<<n_tiles, SK_THREADS, 0, c->st>>>(b, d_cnt_s.p, d_cnt_m.p, nullptr, nullptr, nullptr, nullptr,
+                                                            d_masks.p);
     CK(cudaGetLastError());
     c->launches++;
     exclusive_scan_u32(c, d_cnt_s.p, d_off_s.p, n_warps + 1);
@@ -264,8 +266,12 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     // per-genome seed offsets = scanned offsets at genome tile boundaries
     std::vector<uint32_t> h_off_s(nb + 1);
     uint32_t tot_m = 0;
-    for (int32_t i = 0; i <= nb; i++)
-        CK(cudaMemcpyAsync(&h_off_s[i], d_off_s.p + (size_t)tile_off[i] * SK_WARPS, 4, cudaMemcpyDeviceToHost, c->st));
+    PoolRef<uint32_t> d_goff(c->pool["sketch_batch.d_goff"]);
+    d_goff.reserve((size_t)nb + 1, 0, c->st);
+    gather_strided_kernel<<<nblk((uint64_t)nb + 1, 256), 256, 0, c->st>>>(d_off_s.p, d_tile_off.p, SK_WARPS, nb + 1, d_goff.p);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpyAsync(h_off_s.data(), d_goff.p, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(&tot_m, d_off_m.p + n_warps, 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     const uint64_t cur_seeds = c->h_seed_off.back();
@@ -273,7 +279,8 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     c->d_seeds.reserve(cur_seeds + tot_s + 1, cur_seeds, c->st);
     c->d_mkeys.reserve(c->n_mkeys + tot_m + 1, c->n_mkeys, c->st);
     sketch_kernel<true><<<n_tiles, SK_THREADS, 0, c->st>>>(b, nullptr, nullptr, d_off_s.p, d_off_m.p,
-                                                           c->d_seeds.p + cur_seeds, c->d_mkeys.p + c->n_mkeys);
+                                                           c->d_seeds.p + cur_seeds, c->d_mkeys.p + c->n_mkeys,
+                                                           d_masks.p);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaStreamSynchronize(c->st));  // batch-local buffers die here
@@ -530,6 +537,8 @@ void skb_destroy(skb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (cudaEvent_t e : ctx->anchor_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
+    if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->st) {
@@ -595,17 +604,52 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
             if ((uint64_t)p->n_bases + (uint64_t)p->n_contigs * CONTIG_PAD >= (1ull << 31))
                 return fail(ctx, SKB_ELIMIT, "genome too large for 31-bit padded coordinates");
         }
-        // batches of <= 1 Gi bases: per-batch seed/marker totals stay far below 2^32
+        // batches of <= 1 Gi bases (per-batch seed/marker totals stay far below 2^32), grouped into
+        // super-batches of <= 8 whose H2D copies are all enqueued up front on a second stream: batch i+1
+        // uploads while batch i is being sketched.
+        if (!ctx->st_copy) CK(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+        PoolRef<uint64_t> d_packed(ctx->pool["add_genomes.d_packed"]);
         int32_t g0 = 0;
         while (g0 < n) {
-            uint64_t bases = 0;
-            int32_t g1 = g0;
-            while (g1 < n && (g1 == g0 || bases + (uint64_t)genomes[g1]->n_bases <= (1ull << 30))) {
-                bases += (uint64_t)genomes[g1]->n_bases;
-                g1++;
+            std::vector<int32_t> cut{g0};
+            std::vector<uint64_t> woff{0};
+            int32_t g = g0;
+            while (g < n && cut.size() <= 8) {
+                uint64_t bases = 0, words = 0;
+                int32_t g1 = g;
+                while (g1 < n && (g1 == g || bases + (uint64_t)genomes[g1]->n_bases <= (1ull << 30))) {
+                    bases += (uint64_t)genomes[g1]->n_bases;
+                    words += (uint64_t)genomes[g1]->n_words;
+                    g1++;
+                }
+                cut.push_back(g1);
+                woff.push_back(woff.back() + words);
+                g = g1;
             }
-            sketch_batch(ctx, genomes, g0, g1);
-            g0 = g1;
+            const size_t nbatch = cut.size() - 1;
+            CK(cudaStreamSynchronize(ctx->st));  // previous users of the packed buffer are done
+            d_packed.reserve(woff.back() + 2, 0, ctx->st);
+            while (ctx->up_ev.size() < nbatch) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->up_ev.push_back(e);
+            }
+            for (size_t bi = 0; bi < nbatch; bi++) {
+                uint64_t w = woff[bi];
+                for (int32_t i = cut[bi]; i < cut[bi + 1];) {  // genomes adjacent in host memory go up as one copy
+                    int32_t j = i + 1;
+                    uint64_t words = (uint64_t)genomes[i]->n_words;
+                    while (j < cut[bi + 1] && genomes[j]->words == genomes[i]->words + words) words += (uint64_t)genomes[j++]->n_words;
+                    CK(cudaMemcpyAsync(d_packed.p + w, genomes[i]->words, (size_t)words * 8, cudaMemcpyHostToDevice,
+                                       ctx->st_copy));
+                    w += words;
+                    i = j;
+                }
+                CK(cudaEventRecord(ctx->up_ev[bi], ctx->st_copy));
+            }
+            for (size_t bi = 0; bi < nbatch; bi++)
+                sketch_batch(ctx, genomes, cut[bi], cut[bi + 1], d_packed.p + woff[bi], ctx->up_ev[bi]);
+            g0 = cut.back();
         }
         return SKB_OK;
     });

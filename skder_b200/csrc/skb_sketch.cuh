@@ -9,9 +9,10 @@
 // (512 contiguous bytes per request), a CTA 16384.  The 20 bases of left context come from the
 // neighbouring lane by shuffle (lane 0 re-reads one word).  Phase A rolls the forward and
 // reverse-complement 21-mer windows and hashes both k-mers at every valid position, keeping two
-// 64-bit hit masks in registers; phase B (emit pass only) turns the mask bits into records at
-// offsets fixed by a warp prefix sum + the scanned per-warp counts, so seeds come out in position
-// order with no sort.
+// 64-bit hit masks; the hash pass stores them (16 bytes per lane) next to the per-warp counts, and
+// the emit pass -- after the counts are scanned -- reads the masks back instead of hashing again and
+// turns the mask bits into records at offsets fixed by a warp prefix sum + the scanned per-warp
+// counts, so seeds come out in position order with no sort.
 #pragma once
 #include "skb_common.cuh"
 
@@ -45,7 +46,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(SK_THREADS)
 sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__restrict__ warp_marker_cnt,
               const uint32_t *__restrict__ warp_seed_off, const uint32_t *__restrict__ warp_marker_off,
-              uint64_t *__restrict__ seeds_out, uint64_t *__restrict__ mkeys_out) {
+              uint64_t *__restrict__ seeds_out, uint64_t *__restrict__ mkeys_out, ulonglong2 *__restrict__ masks) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // genome of this CTA: last g with tile_off[g] <= blockIdx.x
     int lo = 0, hi = b.n - 1;
@@ -75,7 +76,12 @@ sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__r
     const uint64_t *cs = b.ctg_start + b.g_ctg_off[g];
     const int nc = (int)(b.g_ctg_off[g + 1] - b.g_ctg_off[g]);
     int ci0 = 0;
-    if (p0 < nb) {
+    if (EMIT) {  // the hash pass left this lane's two hit masks behind: no second round of hashing
+        const ulonglong2 mk = masks[wgid * 32 + lane];
+        seed_mask = mk.x;
+        marker_mask = mk.y;
+    }
+    if (p0 < nb && (!EMIT || (seed_mask | marker_mask) != 0)) {
         int l2 = 0, h2 = nc - 1;  // last contig with start <= p0
         while (l2 < h2) {
             int mid = (l2 + h2 + 1) >> 1;
@@ -85,6 +91,8 @@ sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__r
                 h2 = mid - 1;
         }
         ci0 = l2;
+    }
+    if (!EMIT && p0 < nb) {
         int ci = ci0;
         uint64_t cstart = cs[ci];
         uint64_t cnext = (ci + 1 < nc) ? cs[ci + 1] : nb;
@@ -120,6 +128,7 @@ sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__r
     }
     const int ns = __popcll(seed_mask), nm = __popcll(marker_mask);
     if (!EMIT) {
+        masks[wgid * 32 + lane] = make_ulonglong2(seed_mask, marker_mask);
         const unsigned ts = __reduce_add_sync(0xffffffffu, (unsigned)ns);
         const unsigned tm = __reduce_add_sync(0xffffffffu, (unsigned)nm);
         if (lane == 0) {
@@ -172,6 +181,13 @@ sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__r
             }
         }
     }
+}
+
+// out[i] = src[idx[i] * mult]: the scanned per-warp offsets at every genome's first tile
+__global__ void gather_strided_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t mult,
+                                      int n, uint32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[(size_t)idx[i] * mult];
 }
 
 }  // namespace skb

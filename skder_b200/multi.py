@@ -71,25 +71,26 @@ def replicate_sketches(eng, dist, torch):
 
 
 def gather_edges(edges, dist, torch, device=None):
-    """Variable-length edge arrays of all ranks -> one array sorted by (a, b) on rank 0 (empty elsewhere)."""
+    """Variable-length edge arrays of all ranks -> one array sorted by (a, b) on rank 0 (empty elsewhere).
+    Two small collectives: the counts, then one padded gather of the raw 32-byte records."""
     world, rank = dist.get_world_size(), dist.get_rank()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    n = torch.tensor([len(edges)], dtype=torch.int64, device=device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, torch.tensor([len(edges)], dtype=torch.int64, device=device))
+    counts = counts.tolist()
     mx = max(max(counts), 1)
-    buf = np.zeros(mx, EDGE_DTYPE)
-    buf[: len(edges)] = edges
-    send = torch.from_numpy(buf.view(np.uint8).copy()).to(device)
-    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-    dist.gather(send, recv, dst=0)
+    send = torch.zeros(mx * EDGE_DTYPE.itemsize, dtype=torch.uint8, device=device)
+    if len(edges):
+        send[: len(edges) * EDGE_DTYPE.itemsize].copy_(torch.from_numpy(np.ascontiguousarray(edges).view(np.uint8)))
+    recv = torch.empty(world * mx * EDGE_DTYPE.itemsize, dtype=torch.uint8, device=device) if rank == 0 else None
+    dist.gather(send, list(recv.chunk(world)) if rank == 0 else None, dst=0)
     if rank != 0:
         return np.zeros(0, EDGE_DTYPE)
-    parts = [r.cpu().numpy().view(EDGE_DTYPE)[:c] for r, c in zip(recv, counts)]
-    out = np.concatenate(parts) if parts else np.zeros(0, EDGE_DTYPE)
-    return np.sort(out, order=["a", "b"])
+    flat = recv.cpu().numpy().view(EDGE_DTYPE).reshape(world, mx)
+    out = np.concatenate([flat[r, :c] for r, c in enumerate(counts)])
+    key = (out["a"].astype(np.uint64) << np.uint64(32)) | out["b"].astype(np.uint64)
+    return out[np.argsort(key, kind="stable")]
 
 
 def partition_rows(n, part, n_parts):
