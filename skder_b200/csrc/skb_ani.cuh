@@ -138,7 +138,7 @@ __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, 
 
 // ---- K4a: anchors.  One warp per task; the only dependent reads are descriptor -> seed records ->
 // buckets, covered by the other resident warps.
-__global__ void __launch_bounds__(ANC_THREADS, 2)
+__global__ void __launch_bounds__(ANC_THREADS, 4)
 anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint32_t n_tasks,
               uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n) {
     __shared__ uint32_t stage_all[ANC_THREADS / 32][32 * STAGE];

@@ -31,15 +31,18 @@ constexpr uint64_t GID_MASK = (1ull << GID_BITS) - 1;
 
 constexpr uint64_t TAB_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
-// minimap2/skani invertible 64-bit mix; first line is ~(key + (key << 21)) (see oracle)
+// minimap2/skani invertible 64-bit mix; first line is ~(key + (key << 21)) (see oracle).  The shift-add
+// steps are written as the multiplications they are (x + (x<<3) + (x<<8) = 265 x, ...): identical mod
+// 2^64, but they issue on the FMA pipe (IMAD) instead of piling 64-bit shifts/adds on the ALU pipe,
+// which is what bounded the sketch kernel (ncu: 39% math-pipe throttle).
 __host__ __device__ inline uint64_t mm_hash64(uint64_t key) {
-    key = ~(key + (key << 21));
+    key = ~(key * 0x200001ull);
     key = key ^ (key >> 24);
-    key = (key + (key << 3)) + (key << 8);
+    key = key * 265ull;
     key = key ^ (key >> 14);
-    key = (key + (key << 2)) + (key << 4);
+    key = key * 21ull;
     key = key ^ (key >> 28);
-    key = key + (key << 31);
+    key = key * 0x80000001ull;
     return key;
 }
 

@@ -14,7 +14,7 @@
 
 namespace skb {
 
-constexpr int PJ = 4;         // lookups in flight per lane in the batched probe
+constexpr int PJ = 2;         // lookups in flight per lane in the batched probe
 constexpr int STAGE_CAP = 8;  // hits staged per seed (max_mult upper bound)
 
 __host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
