@@ -8,7 +8,8 @@ A step = one pass of the hot path over one synthetic genome set (BASELINE.json c
   value : pairs/s with sketches already resident in HBM (prescreen + ANI/AF + edge gather), device-timed
   e2e   : pairs/s through the C-ABI from packed genomes in pinned HOST memory to edges on the host
           (H2D upload + sketch + index + prescreen + ANI/AF + D2H), every step.
-N=1 runs BASELINE configs[1] (1,000 x 5 Mbp, greedy thresholds); N>1 shards the same triangle's rows
+The workload is the configuration BASELINE.json quotes its metric on (N=5k x 5 Mbp = configs[2], `config3`; it fits one GPU);
+N>1 shards the same triangle's rows
 round-robin over the ranks (no data-path collective; sketches are replicated by NCCL all-gather
 before the timed region of `value`, inside it for `e2e`).
 """
@@ -371,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--workload", default="config3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
