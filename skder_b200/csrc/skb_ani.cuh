@@ -28,7 +28,7 @@
 namespace skb {
 
 constexpr int LB = 16;                        // DP look-back in anchors
-constexpr int DP_UNR = 2;                     // anchors per DP iteration (code size vs register moves)
+constexpr int DP_UNR = 4;                     // anchors per DP iteration (code size vs register moves)
 constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA pass
 constexpr int DP_THREADS = 128;               // K4b: one task per thread
 constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA pass
@@ -186,7 +186,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
     if (w_n == 0) return;
     constexpr int UNR = DP_UNR;
-    static_assert(UNR == 2, "the anchor prefetch below moves 16 bytes per iteration");
+    static_assert(UNR % 2 == 0 && MAXA % UNR == 0, "anchors are fetched 16 bytes at a time");
     int Q[LB + UNR], D[LB + UNR], F[LB + UNR];
     uint32_t RC[LB + UNR];
 #pragma unroll
@@ -200,12 +200,20 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     const uint64_t *ap = anc_all + (size_t)tt * MAXA;
     uint32_t *rp = res_all + (size_t)tt * MAXA;
     const unsigned band = (unsigned)prm.band_bp;
-    ulonglong2 vnext = __ldcg(reinterpret_cast<const ulonglong2 *>(ap));
+    ulonglong2 vnext[UNR / 2];
+#pragma unroll
+    for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap) + x);
     for (int i0 = 0; i0 < w_n; i0 += UNR) {
         uint64_t av[UNR];
-        av[0] = vnext.x;
-        av[1] = vnext.y;
-        if (i0 + UNR < MAXA) vnext = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR));  // next iteration's anchors
+#pragma unroll
+        for (int x = 0; x < UNR / 2; x++) {
+            av[2 * x] = vnext[x].x;
+            av[2 * x + 1] = vnext[x].y;
+        }
+        if (i0 + UNR < MAXA) {  // next iteration's anchors
+#pragma unroll
+            for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR) + x);
+        }
         uint32_t outp[UNR];
 #pragma unroll
         for (int x = 0; x < UNR; x++) {
@@ -238,7 +246,11 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             F[me] = live ? best + prm.anchor_score : -(1 << 24);
             RC[me] = rci;
         }
-        if (i0 < my_n) __stcg(reinterpret_cast<uint2 *>(rp + i0), make_uint2(outp[0], outp[1]));
+        if (i0 < my_n) {
+#pragma unroll
+            for (int x = 0; x < UNR / 2; x++)
+                __stcg(reinterpret_cast<uint2 *>(rp + i0) + x, make_uint2(outp[2 * x], outp[2 * x + 1]));
+        }
 #pragma unroll
         for (int u = LB + UNR - 1; u >= UNR; u--) {
             Q[u] = Q[u - UNR];
@@ -489,30 +501,38 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         __syncthreads();
         if (tid == 0) ctl.unresolved = 0;
         __syncthreads();
-        for (int t = tid; t < nc; t += FIN_THREADS) {
-            if (state[t]) continue;
-            const Cand &c = cands[(int)(skey[t] & 0xfff)];
-            const long long lq = (long long)c.q1 - c.q0 + 1, lr = (long long)c.r1 - c.r0 + 1;
-            int verdict = 1;
-            for (int u = 0; u < t; u++) {
-                const uint8_t su = ((volatile uint8_t *)state)[u];
-                if (su == 2) continue;
-                const Cand &d = cands[(int)(skey[u] & 0xfff)];
-                const long long oq = (long long)(c.q1 < d.q1 ? c.q1 : d.q1) - (long long)(c.q0 > d.q0 ? c.q0 : d.q0) + 1;
-                const long long orr = (long long)(c.r1 < d.r1 ? c.r1 : d.r1) - (long long)(c.r0 > d.r0 ? c.r0 : d.r0) + 1;
-                const bool blocks = (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) ||
-                                    (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
-                if (!blocks) continue;
-                if (su == 1) {
-                    verdict = 2;
-                    break;
+        // rank t costs t comparisons: give every thread one cheap and one expensive rank (tt, nc-1-tt)
+        for (int w0 = tid; 2 * w0 < nc; w0 += FIN_THREADS) {
+            for (int side = 0; side < 2; side++) {
+                const int t = side ? nc - 1 - w0 : w0;
+                if (side && t == w0) break;
+                if (state[t]) continue;
+                const uint4 cr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[t] & 0xfff)]);  // q0 q1 r0 r1
+                const long long lq = (long long)cr.y - cr.x + 1, lr = (long long)cr.w - cr.z + 1;
+                int verdict = 1;
+                for (int u = 0; u < t; u++) {
+                    const uint4 dr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[u] & 0xfff)]);
+                    // intervals that do not even touch (the usual case) cannot block: two compares each
+                    const bool tq = dr.x <= cr.y && cr.x <= dr.y, tr = dr.z <= cr.w && cr.z <= dr.w;
+                    if (!tq && !tr) continue;
+                    const uint8_t su = ((volatile uint8_t *)state)[u];
+                    if (su == 2) continue;
+                    const long long oq = (long long)(cr.y < dr.y ? cr.y : dr.y) - (long long)(cr.x > dr.x ? cr.x : dr.x) + 1;
+                    const long long orr = (long long)(cr.w < dr.w ? cr.w : dr.w) - (long long)(cr.z > dr.z ? cr.z : dr.z) + 1;
+                    const bool blocks = (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) ||
+                                        (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
+                    if (!blocks) continue;
+                    if (su == 1) {
+                        verdict = 2;
+                        break;
+                    }
+                    verdict = 0;  // blocked by an undecided candidate: wait
                 }
-                verdict = 0;  // blocked by an undecided candidate: wait
+                if (verdict)
+                    ((volatile uint8_t *)state)[t] = (uint8_t)verdict;
+                else
+                    ctl.unresolved = 1;
             }
-            if (verdict)
-                ((volatile uint8_t *)state)[t] = (uint8_t)verdict;
-            else
-                ctl.unresolved = 1;
         }
         __syncthreads();
         if (!ctl.unresolved) break;

@@ -235,3 +235,69 @@ def test_full_size_properties(built_lib):
         for g in range(8):
             s = e.sizes(g)
             assert abs(s["n_seeds"] / (s["total_len"] / 125.0) - 1) < 0.03
+
+
+def test_edge_cases_through_the_abi(oracle, built_lib):
+    """empty / tiny / all-N genomes, single genome, re-index after adding, clear and reuse, bad arguments"""
+    from skder_b200 import engine
+
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    big = bytes(acgt[rng.integers(0, 4, 120_000)])
+    mut = bytearray(big)
+    for p in rng.integers(0, len(mut), 1200):
+        mut[p] = b"ACGT"[(b"ACGT".index(mut[p]) + 1) % 4]
+    contig_sets = [
+        [],                                   # no contigs at all
+        [b"ACGTTGCA" * 50],                   # 400 bp: below min_contig_len, dropped
+        [b"N" * 3000],                        # packs as poly-A
+        [big],
+        [bytes(mut[:50_000]), bytes(mut[50_000:])],
+        [b"acgt" * 200 + big[:5000].lower()],  # lowercase
+    ]
+    sk = [oracle.Sketch.from_contigs(c) for c in contig_sets]
+    with engine.Engine(0) as e:
+        e.add([engine.pack_contigs(contig_sets[3])])
+        e.index()
+        edges, st = e.triangle(80.0, 0.0)  # a single genome: no pairs
+        assert len(edges) == 0 and st.n_pairs_total == 0
+        with pytest.raises(engine.SkbError):
+            e.pairs_detail([0], [0])
+        with pytest.raises(engine.SkbError):
+            e.rect([0], [5])
+        e.clear()
+        assert e.n_genomes == 0
+        with pytest.raises(engine.SkbError):
+            e.index()  # nothing to index
+        e.add([engine.pack_contigs(c) for c in contig_sets[:4]])
+        with pytest.raises(engine.SkbError):
+            e.triangle(80.0, 0.0)  # not indexed yet
+        e.index()
+        e.add([engine.pack_contigs(c) for c in contig_sets[4:]])  # more genomes after an index
+        with pytest.raises(engine.SkbError):
+            e.triangle(80.0, 0.0)  # stale index is refused
+        e.index()
+        assert e.n_genomes == 6
+        for g, s in enumerate(sk):
+            assert np.array_equal(e.seeds(g), s.seeds()), g
+            assert np.array_equal(e.markers(g), s.markers()), g
+            assert e.sizes(g)["n_chunks"] == s.n_chunks and e.sizes(g)["total_len"] == s.total_len
+        pairs = list(itertools.combinations(range(6), 2))
+        det = e.pairs_detail([p[0] for p in pairs], [p[1] for p in pairs])
+        for (i, j), d in zip(pairs, det):
+            r = oracle.pair(sk[i], sk[j])
+            assert (d.n_chains, d.n_anchors, d.n_seeds, d.span_q, d.span_r) == (
+                r.n_chains, r.n_anchors_total, r.n_seeds_total, r.span_q, r.span_r), (i, j)
+            assert (d.ani < 0) == (r.ani < 0)
+            if r.ani >= 0:
+                assert abs(d.ani - r.ani) < 1e-12
+        got = e.shared_markers([p[0] for p in pairs], [p[1] for p in pairs])
+        assert list(got) == [oracle.screen(sk[i], sk[j], 0.8)[0] for i, j in pairs]
+        # screening off (-s 0): every pair is evaluated; only pairs with an estimate become edges
+        edges, st = e.triangle(0.0, 0.0)
+        assert st.n_pairs_screened == 15
+        want = {(i, j) for i, j in pairs if oracle.pair(sk[i], sk[j]).ani >= 0}
+        assert {(int(x["a"]), int(x["b"])) for x in edges} == want and (3, 4) in want
+        # empty id lists
+        edges, st = e.rect([], [1, 2])
+        assert len(edges) == 0
