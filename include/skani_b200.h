@@ -85,6 +85,13 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes);
  * over every genome added so far.  Must be called before triangle/rect; may be called again after
  * more genomes were added. */
 int skb_index(skb_ctx *ctx);
+/* Index the genomes added since the last skb_index / skb_index_append as QUERY-ONLY additions (seed
+ * tables, chunk tables, marker lists appended; inverted index untouched): they may be queries of skb_rect,
+ * not references and not part of a triangle.  With skb_pop_last_add this is `skani search` (skder.py:119)
+ * against a resident database: one query genome comes and goes at the cost of its own sketch. */
+int skb_index_append(skb_ctx *ctx);
+/* Undo the most recent skb_add_genomes call (only genomes that are not in the inverted index). */
+int skb_pop_last_add(skb_ctx *ctx);
 int32_t skb_n_genomes(const skb_ctx *ctx);
 /* drop every genome and index but keep the device allocations (repeated runs on one context) */
 int skb_clear(skb_ctx *ctx);

@@ -104,7 +104,7 @@ SYMBOLS = [
     "skb_create", "skb_destroy", "skb_last_error", "skb_add_genomes", "skb_index", "skb_n_genomes",
     "skb_sketch_sizes", "skb_get_seeds", "skb_get_markers", "skb_db_save", "skb_db_load", "skb_triangle",
     "skb_rect", "skb_pairs_detail", "skb_shared_markers", "skb_sketch_view_get", "skb_import_sketches",
-    "skb_free", "skb_launch_count", "skb_stream", "skb_clear", "skb_timer_start", "skb_timer_stop",
+    "skb_free", "skb_launch_count", "skb_stream", "skb_clear", "skb_timer_start", "skb_timer_stop", "skb_index_append", "skb_pop_last_add",
 ]
 
 _lib = None
@@ -160,6 +160,8 @@ def lib():
         C.c_void_p,
     ]
     L.skb_clear.argtypes = [C.c_void_p]
+    L.skb_index_append.argtypes = [C.c_void_p]
+    L.skb_pop_last_add.argtypes = [C.c_void_p]
     L.skb_timer_start.argtypes = [C.c_void_p]
     L.skb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.skb_free.argtypes = [C.c_void_p]

@@ -139,19 +139,42 @@ def run_sketch(opt, engine_mod):
 
 
 def run_search(opt, engine_mod):
+    """`skani search q.fa -d DB -o OUT` (reference src/skDER/skder.py:119).  Served by the database's resident
+    daemon (skder_b200/daemon.py; started here on first use) unless SKB_NO_DAEMON=1, in which case the database is
+    loaded, indexed and searched in this process."""
     query = opt["positional"][0]
+    dev = _device()
+    if os.environ.get("SKB_NO_DAEMON") != "1":
+        import subprocess
+
+        from . import daemon
+
+        msg = {"op": "search", "query": query, "screen": opt["screen"], "min_af": opt["min_af"], "out": opt["out"]}
+        rep = daemon.request(opt["db"], dev, msg)
+        if rep is None:
+            log = open(os.path.join(opt["db"], "skani_b200_daemon.log"), "a")
+            subprocess.Popen([sys.executable, "-m", "skder_b200.daemon", opt["db"], str(dev)], stdout=log, stderr=log,
+                             stdin=subprocess.DEVNULL, start_new_session=True,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            deadline = time.time() + float(os.environ.get("SKB_DAEMON_START_TIMEOUT", "600"))
+            while rep is None and time.time() < deadline:
+                time.sleep(0.2)
+                if daemon.request(opt["db"], dev, {"op": "ping"}, timeout=5.0):
+                    rep = daemon.request(opt["db"], dev, msg)
+        if rep is None:
+            raise RuntimeError("search daemon did not come up (see %s/skani_b200_daemon.log)" % opt["db"])
+        if not rep.get("ok"):
+            raise RuntimeError("search daemon: %s" % rep.get("error"))
+        return None
     with open(os.path.join(opt["db"], "manifest.json")) as f:
         man = json.load(f)
     paths, names = list(man["paths"]), list(man["names"])
-    with engine_mod.Engine(_device()) as eng:
+    with engine_mod.Engine(dev) as eng:
         eng.load(opt["db"])
-        qp = eng.add_fasta([query], threads=1)
-        paths.append(query)
-        names.append(qp[0].first_name)
         eng.index()
-        qid = eng.n_genomes - 1
-        edges, st = eng.rect(list(range(qid)), [qid], screen=opt["screen"], min_af=opt["min_af"])
-    write_atomic(opt["out"], HEADER + "".join(rect_rows(paths, names, edges)))
+        qp = engine_mod.pack_fasta(query, eng.params.min_contig_len)
+        edges, st = eng.search(qp, screen=opt["screen"], min_af=opt["min_af"])
+    write_atomic(opt["out"], HEADER + "".join(rect_rows(paths + [query], names + [qp.first_name], edges)))
     return st
 
 

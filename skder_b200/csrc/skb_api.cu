@@ -117,6 +117,12 @@ struct skb_ctx {
     DevBuf<uint32_t> d_chunk_begin, d_chunk_start, d_chunk_len, d_chunk_off, d_ctg_pstart, d_ctg_len, d_ctg_off,
         d_marker_cnt;
     std::vector<uint64_t> h_marker_off;    // [n+1]
+    std::vector<uint64_t> h_tab_off{0};    // [n_indexed+1]
+    std::vector<uint32_t> h_tab_buckets, h_ctg_pstart, h_chunk_start, h_chunk_len;
+    int32_t n_inv_genomes = 0;             // genomes covered by the inverted marker index
+    uint64_t n_mkeys_indexed = 0;          // raw marker keys consumed by the last (append) index
+    struct AddCall { int32_t n_before; uint64_t mkeys_before; };
+    std::vector<AddCall> add_calls;        // for skb_pop_last_add
     std::vector<uint32_t> h_chunk_off;     // [n+1]
     uint64_t n_inv = 0;
     // scratch
@@ -565,6 +571,14 @@ int skb_clear(skb_ctx *ctx) {
         ctx->indexed = false;
         ctx->n_indexed = 0;
         ctx->n_inv = 0;
+        ctx->n_inv_genomes = 0;
+        ctx->n_mkeys_indexed = 0;
+        ctx->add_calls.clear();
+        ctx->h_tab_off.assign(1, 0);
+        ctx->h_tab_buckets.clear();
+        ctx->h_ctg_pstart.clear();
+        ctx->h_chunk_start.clear();
+        ctx->h_chunk_len.clear();
         return SKB_OK;
     });
 }
@@ -607,6 +621,7 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
         // batches of <= 1 Gi bases (per-batch seed/marker totals stay far below 2^32), grouped into
         // super-batches of <= 8 whose H2D copies are all enqueued up front on a second stream: batch i+1
         // uploads while batch i is being sketched.
+        ctx->add_calls.push_back({ctx->n(), ctx->n_mkeys});
         if (!ctx->st_copy) CK(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
         PoolRef<uint64_t> d_packed(ctx->pool["add_genomes.d_packed"]);
         int32_t g0 = 0;
@@ -662,9 +677,14 @@ int skb_index(skb_ctx *ctx) {
         if (n == 0) return fail(c, SKB_ESTATE, "no genomes added");
         const uint64_t n_seeds = c->h_seed_off.back();
         // ---- host-side tables: seed hash sizes, contigs in padded coordinates, chunks
-        std::vector<uint64_t> tab_off(n + 1, 0);
-        std::vector<uint32_t> tab_buckets(n);
-        std::vector<uint32_t> ctg_pstart(c->h_ctg_len.size()), chunk_start, chunk_len;
+        std::vector<uint64_t> &tab_off = c->h_tab_off;
+        std::vector<uint32_t> &tab_buckets = c->h_tab_buckets, &ctg_pstart = c->h_ctg_pstart, &chunk_start = c->h_chunk_start,
+                              &chunk_len = c->h_chunk_len;
+        tab_off.assign(n + 1, 0);
+        tab_buckets.assign(n, 0);
+        ctg_pstart.assign(c->h_ctg_len.size(), 0);
+        chunk_start.clear();
+        chunk_len.clear();
         c->h_chunk_off.assign(n + 1, 0);
         for (int32_t g = 0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
@@ -698,17 +718,17 @@ int skb_index(skb_ctx *ctx) {
         CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
         if (n_seeds) {
             tab_insert_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n,
-                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_buckets.p);
+                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_buckets.p, 0);
             CK(cudaGetLastError());
             rep_flag_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n, c->d_tab.p,
-                                                                  c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult);
+                                                                  c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult, 0);
             CK(cudaGetLastError());
             c->launches += 3;
         }
         const uint32_t n_entries = (uint32_t)chunk_start.size() + (uint32_t)n;
         c->d_chunk_begin.reserve(n_entries, 0, c->st);
         chunk_begin_kernel<<<nblk(n_entries, 256), 256, 0, c->st>>>(c->d_seeds.p, c->d_seed_off.p, c->d_chunk_off.p, n,
-                                                                   c->d_chunk_start.p, c->d_chunk_begin.p, n_entries);
+                                                                   c->d_chunk_start.p, c->d_chunk_begin.p, n_entries, 0);
         CK(cudaGetLastError());
         c->launches++;
         // ---- markers: sort raw keys, unique -> inverted index; per-genome counts; per-genome lists
@@ -753,7 +773,155 @@ int skb_index(skb_ctx *ctx) {
         c->d_marker_off.upload(c->h_marker_off, c->st);
         CK(cudaStreamSynchronize(c->st));
         c->n_indexed = n;
+        c->n_inv_genomes = n;
+        c->n_mkeys_indexed = c->n_mkeys;
         c->indexed = true;
+        return SKB_OK;
+    });
+}
+
+// Index the genomes added since the last skb_index / skb_index_append as QUERY-ONLY additions: their
+// seed tables, repeat flags, chunk tables and sorted marker lists are appended; the inverted marker
+// index is left alone (they can be the query side of skb_rect, not a reference, and not part of a
+// triangle).  This is what `skani search` needs: the database stays resident and indexed, one query
+// genome comes and goes (skb_pop_last_add) at the cost of its own sketch.
+int skb_index_append(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        const int32_t n = c->n(), n0 = c->n_indexed;
+        if (!c->indexed && n0 == 0) return fail(c, SKB_ESTATE, "call skb_index on the database first");
+        if (n == n0) {
+            c->indexed = true;
+            return SKB_OK;
+        }
+        const uint64_t seeds0 = c->h_seed_off[n0], seeds1 = c->h_seed_off[n];
+        const size_t ctg0 = c->h_ctg_off[n0], chunks0 = c->h_chunk_start.size();
+        c->h_tab_off.resize(n + 1);
+        c->h_tab_buckets.resize(n);
+        c->h_ctg_pstart.resize(c->h_ctg_len.size());
+        c->h_chunk_off.resize(n + 1);
+        for (int32_t g = n0; g < n; g++) {
+            const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
+            if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
+            c->h_tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns / 2 + 1);
+            c->h_tab_off[g + 1] = c->h_tab_off[g] + (uint64_t)c->h_tab_buckets[g] * BUCKET;
+            uint32_t off = 0;
+            for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
+                c->h_ctg_pstart[k] = off;
+                const uint32_t len = c->h_ctg_len[k];
+                for (uint32_t st = 0; st < len; st += (uint32_t)c->prm.chunk_len) {
+                    c->h_chunk_start.push_back(off + st);
+                    c->h_chunk_len.push_back(std::min<uint32_t>((uint32_t)c->prm.chunk_len, len - st));
+                }
+                off += len + CONTIG_PAD;
+            }
+            c->h_chunk_off[g + 1] = (uint32_t)c->h_chunk_start.size();
+        }
+        auto append = [&](auto &dev, const auto &host, size_t old_n) {
+            dev.reserve(std::max<size_t>(host.size(), 1), old_n, c->st);
+            if (host.size() > old_n)
+                CK(cudaMemcpyAsync(dev.p + old_n, host.data() + old_n, (host.size() - old_n) * sizeof(host[0]),
+                                   cudaMemcpyHostToDevice, c->st));
+        };
+        append(c->d_seed_off, c->h_seed_off, (size_t)n0 + 1);
+        append(c->d_tab_off, c->h_tab_off, (size_t)n0 + 1);
+        append(c->d_tab_buckets, c->h_tab_buckets, (size_t)n0);
+        append(c->d_total_len, c->h_total_len, (size_t)n0);
+        append(c->d_ctg_pstart, c->h_ctg_pstart, ctg0);
+        append(c->d_ctg_len, c->h_ctg_len, ctg0);
+        append(c->d_ctg_off, c->h_ctg_off, (size_t)n0 + 1);
+        append(c->d_chunk_start, c->h_chunk_start, chunks0);
+        append(c->d_chunk_len, c->h_chunk_len, chunks0);
+        append(c->d_chunk_off, c->h_chunk_off, (size_t)n0 + 1);
+        // seed tables + repeat flags of the new genomes only
+        c->d_tab.reserve(c->h_tab_off[n], c->h_tab_off[n0], c->st);
+        CK(cudaMemsetAsync(c->d_tab.p + c->h_tab_off[n0], 0xFF, (c->h_tab_off[n] - c->h_tab_off[n0]) * 8, c->st));
+        if (seeds1 > seeds0) {
+            tab_insert_kernel<<<nblk(seeds1 - seeds0, 256), 256, 0, c->st>>>(c->d_seeds.p, seeds1, c->d_seed_off.p, n, c->d_tab.p,
+                                                                           c->d_tab_off.p, c->d_tab_buckets.p, seeds0);
+            CK(cudaGetLastError());
+            rep_flag_kernel<<<nblk(seeds1 - seeds0, 256), 256, 0, c->st>>>(c->d_seeds.p, seeds1, c->d_seed_off.p, n, c->d_tab.p,
+                                                                         c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult,
+                                                                         seeds0);
+            CK(cudaGetLastError());
+            c->launches += 2;
+        }
+        const uint32_t ent0 = (uint32_t)chunks0 + (uint32_t)n0, ent1 = (uint32_t)c->h_chunk_start.size() + (uint32_t)n;
+        c->d_chunk_begin.reserve(ent1, ent0, c->st);
+        chunk_begin_kernel<<<nblk(ent1 - ent0, 256), 256, 0, c->st>>>(c->d_seeds.p, c->d_seed_off.p, c->d_chunk_off.p, n,
+                                                                     c->d_chunk_start.p, c->d_chunk_begin.p, ent1, ent0);
+        CK(cudaGetLastError());
+        c->launches++;
+        // sorted unique marker lists of the new genomes, appended behind the database's
+        const uint64_t nk = c->n_mkeys - c->n_mkeys_indexed;
+        c->h_marker_off.resize(n + 1);
+        for (int32_t g = n0; g < n; g++) c->h_marker_off[g + 1] = c->h_marker_off[g];
+        c->d_marker_cnt.reserve((size_t)n, (size_t)n0, c->st);
+        CK(cudaMemsetAsync(c->d_marker_cnt.p + n0, 0, (size_t)(n - n0) * 4, c->st));
+        if (nk) {
+            PoolRef<uint64_t> d_a(c->pool["skb_index_append.a"]), d_b(c->pool["skb_index_append.b"]);
+            PoolRef<uint32_t> d_flag(c->pool["skb_index_append.flag"]), d_pos(c->pool["skb_index_append.pos"]);
+            d_a.reserve(nk, 0, c->st);
+            d_b.reserve(nk, 0, c->st);
+            d_flag.reserve(nk + 1, 0, c->st);
+            d_pos.reserve(nk + 1, 0, c->st);
+            swap_key_kernel<<<nblk(nk, 256), 256, 0, c->st>>>(c->d_mkeys.p + c->n_mkeys_indexed, nk, d_a.p);
+            CK(cudaGetLastError());
+            sort_keys_u64(c, d_a.p, d_b.p, nk);
+            unique_flag_kernel<<<nblk(nk, 256), 256, 0, c->st>>>(d_b.p, nk, d_flag.p);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_flag.p + nk, 0, 4, c->st));
+            exclusive_scan_u32(c, d_flag.p, d_pos.p, nk + 1);
+            uint32_t nu = 0;
+            CK(cudaMemcpyAsync(&nu, d_pos.p + nk, 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            const uint64_t m0 = c->h_marker_off[n0];
+            c->d_markers.reserve(m0 + nu + 1, m0, c->st);
+            unique_scatter_swapped_kernel<<<nblk(nk, 256), 256, 0, c->st>>>(d_b.p, nk, d_flag.p, d_pos.p, c->d_markers.p + m0,
+                                                                           c->d_marker_cnt.p);
+            CK(cudaGetLastError());
+            c->launches += 3;
+            std::vector<uint32_t> cnt((size_t)(n - n0));
+            CK(cudaMemcpyAsync(cnt.data(), c->d_marker_cnt.p + n0, cnt.size() * 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            for (int32_t g = n0; g < n; g++) c->h_marker_off[g + 1] = c->h_marker_off[g] + cnt[(size_t)(g - n0)];
+        }
+        append(c->d_marker_off, c->h_marker_off, (size_t)n0 + 1);
+        CK(cudaStreamSynchronize(c->st));
+        c->n_mkeys_indexed = c->n_mkeys;
+        c->n_indexed = n;
+        c->indexed = true;
+        return SKB_OK;
+    });
+}
+
+// Undo the most recent skb_add_genomes call (and its index entries): the query genome of a search leaves.
+int skb_pop_last_add(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (c->add_calls.empty()) return fail(c, SKB_ESTATE, "nothing to pop");
+        const skb_ctx::AddCall a = c->add_calls.back();
+        if (a.n_before < c->n_inv_genomes) return fail(c, SKB_ESTATE, "cannot pop genomes that are part of the inverted index");
+        CK(cudaStreamSynchronize(c->st));
+        c->add_calls.pop_back();
+        const int32_t n = a.n_before;
+        c->h_seed_off.resize(n + 1);
+        c->h_total_len.resize(n);
+        c->h_ctg_off.resize(n + 1);
+        c->h_ctg_len.resize(c->h_ctg_off.back());
+        c->n_mkeys = a.mkeys_before;
+        if (c->n_indexed > n) {
+            c->n_indexed = n;
+            c->h_tab_off.resize(n + 1);
+            c->h_tab_buckets.resize(n);
+            c->h_ctg_pstart.resize(c->h_ctg_len.size());
+            c->h_chunk_off.resize(n + 1);
+            c->h_chunk_start.resize(c->h_chunk_off.back());
+            c->h_chunk_len.resize(c->h_chunk_off.back());
+            c->h_marker_off.resize(n + 1);
+            c->n_mkeys_indexed = std::min(c->n_mkeys_indexed, c->n_mkeys);
+        }
+        c->indexed = c->n_indexed == n && n > 0;
         return SKB_OK;
     });
 }
@@ -798,6 +966,7 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
         skb_ctx *c = ctx;
         if (!edges || !n_edges || n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
         if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        if (c->n_inv_genomes != c->n()) return fail(c, SKB_ESTATE, "query-only genomes present: triangle needs skb_index");
         const uint32_t n = (uint32_t)c->n_indexed;
         const int64_t launches0 = c->launches;
         cudaEvent_t e0, e1, e2;
@@ -883,6 +1052,8 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
         std::vector<int32_t> ref_slot(n, -1);
         for (int32_t i = 0; i < n_refs; i++) {
             if (refs[i] < 0 || refs[i] >= n) return fail(c, SKB_EINVAL, "reference id out of range");
+            if (refs[i] >= c->n_inv_genomes && screen_pct > 0.0)
+                return fail(c, SKB_ESTATE, "a query-only genome (skb_index_append) cannot be a screened reference");
             if (ref_slot[refs[i]] >= 0) return fail(c, SKB_EINVAL, "duplicate reference id");
             ref_slot[refs[i]] = i;
         }

@@ -14,8 +14,8 @@ namespace skb {
 __global__ void chunk_begin_kernel(const uint64_t *__restrict__ seeds, const uint64_t *__restrict__ g_seed_off,
                                    const uint32_t *__restrict__ g_chunk_off, int n_genomes,
                                    const uint32_t *__restrict__ chunk_start, uint32_t *__restrict__ chunk_begin,
-                                   uint32_t total_entries /* total chunks + n_genomes */) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+                                   uint32_t total_entries /* total chunks + n_genomes */, uint32_t first) {
+    uint32_t t = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_entries) return;
     // entry t belongs to genome g where g_chunk_off[g] + g <= t
     int lo = 0, hi = n_genomes - 1;
@@ -68,6 +68,15 @@ __global__ void swap_key_kernel(const uint64_t *__restrict__ inv, uint64_t n, ui
     if (i >= n) return;
     const uint64_t k = inv[i];
     out[i] = ((k & GID_MASK) << (2 * K_MARKER)) | (k >> GID_BITS);
+}
+// sorted (gid << 42 | marker) keys -> markers of the flagged (unique) ones, and per-genome counts
+__global__ void unique_scatter_swapped_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+                                              const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                              uint64_t *__restrict__ out, uint32_t *__restrict__ g_marker_cnt) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    out[pos[i]] = keys[i] & MASK_MARKER;
+    atomicAdd(&g_marker_cnt[keys[i] >> (2 * K_MARKER)], 1u);
 }
 __global__ void strip_gid_kernel(uint64_t *keys, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

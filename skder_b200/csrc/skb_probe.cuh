@@ -40,8 +40,9 @@ __device__ __forceinline__ int genome_of(const uint64_t *__restrict__ off, int n
 // one thread per seed record: insert into its genome's table (64-bit CAS; no deletions ever)
 __global__ void tab_insert_kernel(const uint64_t *__restrict__ seeds, uint64_t n_seeds,
                                   const uint64_t *__restrict__ g_seed_off, int n_genomes, uint64_t *tab,
-                                  const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                  const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets,
+                                  uint64_t first /* records [first, n_seeds) are inserted */) {
+    uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_seeds) return;
     const int g = genome_of(g_seed_off, n_genomes, i);
     const uint32_t nb = g_tab_buckets[g];
@@ -118,8 +119,8 @@ __device__ __forceinline__ int tab_count(const uint64_t *__restrict__ T, uint32_
 __global__ void rep_flag_kernel(uint64_t *seeds, uint64_t n_seeds, const uint64_t *__restrict__ g_seed_off,
                                 int n_genomes, const uint64_t *__restrict__ tab,
                                 const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets,
-                                int max_mult) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                int max_mult, uint64_t first) {
+    uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_seeds) return;
     const int g = genome_of(g_seed_off, n_genomes, i);
     const uint64_t s = seeds[i];

@@ -147,6 +147,23 @@ class Engine:
     def index(self):
         self._ck(self._L.skb_index(self._h), "skb_index")
 
+    def index_append(self):
+        self._ck(self._L.skb_index_append(self._h), "skb_index_append")
+
+    def pop_last_add(self):
+        self._ck(self._L.skb_pop_last_add(self._h), "skb_pop_last_add")
+
+    def search(self, query_packed, screen=80.0, min_af=15.0):
+        """`skani search`: one query genome against the resident, indexed database (ids 0..n-1).  The query
+        is sketched, indexed query-only, compared, and removed again.  Edges: a = database genome, b = query."""
+        n_db = self.n_genomes
+        self.add([query_packed])
+        try:
+            self.index_append()
+            return self.rect(np.arange(n_db, dtype=np.int32), [n_db], screen=screen, min_af=min_af)
+        finally:
+            self.pop_last_add()
+
     @property
     def n_genomes(self):
         return self._L.skb_n_genomes(self._h)

@@ -301,3 +301,58 @@ def test_edge_cases_through_the_abi(oracle, built_lib):
         # empty id lists
         edges, st = e.rect([], [1, 2])
         assert len(edges) == 0
+
+
+def test_engine_search_and_daemon(genomes7, oracle, built_lib, tmp_path, monkeypatch):
+    """`skani search` three ways -- Engine.search on a resident DB, the shim in-process (SKB_NO_DAEMON=1) and the
+    shim through the resident daemon, twice -- all give the oracle's rows; the DB is untouched afterwards."""
+    import subprocess
+    import sys
+
+    from oracle import skani_cpu
+    from skder_b200 import daemon, engine
+
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join(p + "\n" for p in genomes7))
+    db = tmp_path / "db"
+    assert _run_shim(["sketch", "-l", str(lst), "-o", str(db), "-t", "4"]) == 0
+    sk = {p: oracle.Sketch.from_file(p) for p in genomes7}
+
+    def want_rows(q):
+        rows = []
+        for r in genomes7:
+            res = oracle.pair(sk[r], sk[q])
+            if oracle.screen(sk[r], sk[q], 0.8)[1] and res.ani >= 0 and max(res.af_a, res.af_b) >= 0.15:
+                rows.append((r, "%.2f" % (res.ani * 100), "%.2f" % (res.af_a * 100), "%.2f" % (res.af_b * 100)))
+        return sorted(rows)
+
+    with engine.Engine(0) as e:
+        e.load(str(db))
+        e.index()
+        before, _ = e.triangle(80.0, 0.0)
+        for q in (genomes7[1], genomes7[5]):
+            edges, st = e.search(engine.pack_fasta(q))
+            got = sorted((genomes7[int(x["a"])], "%.2f" % x["ani"], "%.2f" % x["af_a"], "%.2f" % x["af_b"]) for x in edges)
+            assert got == want_rows(q) and all(int(x["b"]) == 7 for x in edges)
+            assert e.n_genomes == 7
+        after, _ = e.triangle(80.0, 0.0)
+        assert np.array_equal(before, after)  # the query came and went; the database is unchanged
+
+    def rows_of(path):
+        return sorted((t[0], t[2], t[3], t[4]) for t in (ln.split("\t") for ln in open(path).read().splitlines()[1:]))
+
+    out = tmp_path / "s.tsv"
+    monkeypatch.setenv("SKB_NO_DAEMON", "1")
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "skder_b200", "bin", "skani")
+    assert subprocess.call([sys.executable, shim, "search", genomes7[3], "-d", str(db), "-o", str(out), "-t", "2"]) == 0
+    assert rows_of(out) == want_rows(genomes7[3])
+    monkeypatch.delenv("SKB_NO_DAEMON")
+    monkeypatch.setenv("SKB_DAEMON_IDLE", "120")
+    try:
+        for q in (genomes7[0], genomes7[6], genomes7[0]):
+            out.unlink()
+            assert subprocess.call([sys.executable, shim, "search", q, "-d", str(db), "-o", str(out), "-t", "2"]) == 0
+            assert rows_of(out) == want_rows(q)
+        assert daemon.request(str(db), 0, {"op": "ping"}, timeout=5.0)["n"] == 7  # one server answered all three
+    finally:
+        daemon.request(str(db), 0, {"op": "stop"}, timeout=5.0)
