@@ -110,21 +110,22 @@ struct __align__(16) TaskDesc {
 };
 static_assert(sizeof(TaskDesc) == 32, "desc size");
 
+// task_off: GLOBAL exclusive scan of the chunk counts, pointing at this batch's first pair; base = its value there
 __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-                                  int64_t n_pairs, uint32_t n_tasks, TaskDesc *__restrict__ desc) {
+                                  uint32_t base, int64_t n_pairs, uint32_t n_tasks, TaskDesc *__restrict__ desc) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tasks) return;
     int64_t lo = 0, hi = n_pairs - 1;
     while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;
-        if (task_off[mid] <= t)
+        if (task_off[mid] - base <= t)
             lo = mid;
         else
             hi = mid - 1;
     }
     const PairInfo pi = info[lo];
     TaskDesc d;
-    d.ch = t - task_off[lo];
+    d.ch = t - (task_off[lo] - base);
     const uint32_t choff = db.g_chunk_off[pi.q];
     const uint32_t *cbeg = db.chunk_begin + choff + pi.q;
     const uint32_t sb = cbeg[d.ch];
@@ -421,7 +422,7 @@ constexpr size_t FIN_SMEM_FIXED = sizeof(Cand) * MAXP + 8 * MAXP + MAXP;
 
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-                int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
+                uint32_t base, int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
                 const uint32_t *__restrict__ perm, PairOut *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FinCtl ctl;
@@ -433,7 +434,7 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
     const int64_t p = blockIdx.x;
     if (p >= n_pairs) return;
     const PairInfo pi = info[p];
-    const uint32_t nch = pi.nch, t0 = task_off[p];
+    const uint32_t nch = pi.nch, t0 = task_off[p] - base;
     const uint32_t choff = db.g_chunk_off[pi.q];
     uint32_t *accS = accA + nch;
     int overflow = nch > FIN_MAX_CHUNKS;

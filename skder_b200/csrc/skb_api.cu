@@ -88,7 +88,8 @@ inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t
 
 struct skb_ctx {
     int device = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_a = nullptr, st_b = nullptr;
+    cudaEvent_t ev_anc[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_ready = nullptr;
     std::vector<cudaEvent_t> up_ev;
     skb_params prm;
     std::string err;
@@ -131,8 +132,6 @@ struct skb_ctx {
     DevBuf<int> d_counter;
     DevBuf<PairInfo> d_info;
     DevBuf<uint32_t> d_nch, d_task_off;
-    DevBuf<Cand> d_cands;
-    DevBuf<uint8_t> d_task_ncand;
 
     int32_t n() const { return (int32_t)h_total_len.size(); }
     DbView view() const {
@@ -343,66 +342,129 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                                                                        c->d_nch.p);
     CK(cudaGetLastError());
     c->launches += 11;
-    // batches of pairs whose tasks fit the candidate scratch (<= 8 Mi tasks = 1 GiB of slots)
+    // global task offsets (exclusive scan of the chunk counts in processing order)
+    CK(cudaMemsetAsync(c->d_nch.p + n_pairs, 0, 4, c->st));
+    exclusive_scan_u32(c, c->d_nch.p, c->d_task_off.p, (size_t)n_pairs + 1);
     std::vector<uint32_t> h_nch((size_t)n_pairs);
     CK(cudaMemcpyAsync(h_nch.data(), c->d_nch.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    const uint64_t max_tasks = 8ull << 20;  // x 3 KiB of anchor/result scratch = 24 GiB
-    int64_t p0 = 0;
-    while (p0 < n_pairs) {
-        uint64_t tasks = 0;
-        int64_t p1 = p0;
-        while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) tasks += h_nch[(size_t)p1++];
-        if (tasks >= (1ull << 32)) throw CudaFail{"pair with too many chunks"};
-        const int64_t np = p1 - p0;
-        CK(cudaMemsetAsync(c->d_nch.p + p1, 0, 4, c->st));  // sentinel for the scan (restored below)
-        exclusive_scan_u32(c, c->d_nch.p + p0, c->d_task_off.p, (size_t)np + 1);
-        if (p1 < n_pairs)
-            CK(cudaMemcpyAsync(c->d_nch.p + p1, &h_nch[(size_t)p1], 4, cudaMemcpyHostToDevice, c->st));
+    uint64_t total_tasks = 0;
+    for (uint32_t v : h_nch) total_tasks += v;
+    if (total_tasks >= (1ull << 32)) throw CudaFail{"too many (pair, chunk) tasks in one call"};
+    // Batches of pairs, double-buffered over two streams: the anchor kernel (L2-bound) of batch b+1 runs
+    // while chain/ends/finalize (issue-bound) of batch b run.  <= 8 Mi tasks per batch (24 GiB of scratch).
+    const uint64_t max_tasks = std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + 5) / 6));
+    struct Batch { int64_t p0, p1; uint64_t base, tasks; };
+    std::vector<Batch> batches;
+    {
+        int64_t p0 = 0;
+        uint64_t base = 0;
+        while (p0 < n_pairs) {
+            uint64_t tasks = 0;
+            int64_t p1 = p0;
+            while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) tasks += h_nch[(size_t)p1++];
+            batches.push_back({p0, p1, base, tasks});
+            base += tasks;
+            p0 = p1;
+        }
+    }
+    uint64_t cap = 1;
+    for (const Batch &bt : batches) cap = std::max(cap, bt.tasks);
+    if (!c->st_a) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->st_a, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&c->st_b, cudaStreamNonBlocking, hi));  // the consumer side goes first
+        for (int k = 0; k < 2; k++) {
+            CK(cudaEventCreateWithFlags(&c->ev_anc[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_free[k], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    }
+    const char *names[2][6] = {{"ani0.anc", "ani0.res", "ani0.tn", "ani0.desc", "ani0.cands", "ani0.ncand"},
+                               {"ani1.anc", "ani1.res", "ani1.tn", "ani1.desc", "ani1.cands", "ani1.ncand"}};
+    const int nbuf = batches.size() > 1 ? 2 : 1;
+    uint64_t *b_anc[2];
+    uint32_t *b_res[2];
+    uint16_t *b_tn[2];
+    TaskDesc *b_desc[2];
+    Cand *b_cands[2];
+    uint8_t *b_ncand[2];
+    for (int k = 0; k < nbuf; k++) {
+        PoolRef<uint64_t> r0(c->pool[names[k][0]]);
+        PoolRef<uint32_t> r1(c->pool[names[k][1]]);
+        PoolRef<uint16_t> r2(c->pool[names[k][2]]);
+        PoolRef<TaskDesc> r3(c->pool[names[k][3]]);
+        PoolRef<Cand> r4(c->pool[names[k][4]]);
+        PoolRef<uint8_t> r5(c->pool[names[k][5]]);
+        r0.reserve((size_t)cap * MAXA + 2, 0, c->st);
+        r1.reserve((size_t)cap * MAXA, 0, c->st);
+        r2.reserve((size_t)cap, 0, c->st);
+        r3.reserve((size_t)cap, 0, c->st);
+        r4.reserve((size_t)cap * SLOTS, 0, c->st);
+        r5.reserve((size_t)cap, 0, c->st);
+        b_anc[k] = r0.p;
+        b_res[k] = r1.p;
+        b_tn[k] = r2.p;
+        b_desc[k] = r3.p;
+        b_cands[k] = r4.p;
+        b_ncand[k] = r5.p;
+    }
+    static const int anchor_ctas_per_sm = [] {
+        const char *e = std::getenv("SKB_ANCHOR_CTAS_PER_SM");
+        return e ? std::max(1, atoi(e)) : 3;
+    }();
+    CK(cudaEventRecord(c->ev_ready, c->st));
+    CK(cudaStreamWaitEvent(c->st_a, c->ev_ready, 0));
+    CK(cudaStreamWaitEvent(c->st_b, c->ev_ready, 0));
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        const Batch &bt = batches[bi];
+        const int k = (int)(bi & 1);
+        const int64_t np = bt.p1 - bt.p0;
+        const uint32_t tasks = (uint32_t)bt.tasks, base = (uint32_t)bt.base;
+        if (bi >= 2) CK(cudaStreamWaitEvent(c->st_a, c->ev_free[k], 0));  // buffer k is free again
         if (tasks) {
-            c->d_cands.reserve((size_t)tasks * SLOTS, 0, c->st);
-            c->d_task_ncand.reserve((size_t)tasks, 0, c->st);
-            CK(cudaMemsetAsync(c->d_task_ncand.p, 0, (size_t)tasks, c->st));
-            PoolRef<uint64_t> d_sanc(c->pool["run_ani.scratch_anc"]);
-            PoolRef<uint32_t> d_sres(c->pool["run_ani.scratch_res"]);
-            PoolRef<uint16_t> d_tn(c->pool["run_ani.task_n"]);
-            PoolRef<TaskDesc> d_desc(c->pool["run_ani.task_desc"]);
-            d_sanc.reserve((size_t)tasks * MAXA + 2, 0, c->st);
-            d_sres.reserve((size_t)tasks * MAXA, 0, c->st);
-            d_tn.reserve((size_t)tasks, 0, c->st);
-            d_desc.reserve((size_t)tasks, 0, c->st);
-            task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, d_info_s.p + p0, c->d_task_off.p, np,
-                                                                   (uint32_t)tasks, d_desc.p);
+            CK(cudaMemsetAsync(b_ncand[k], 0, (size_t)tasks, c->st_a));
+            task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st_a>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base,
+                                                                     np, tasks, b_desc[k]);
             CK(cudaGetLastError());
-            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
+            // pipelined: a persistent grid of `anchor_ctas_per_sm` CTAs per SM, so the consumer kernels of the previous
+            // batch find free registers next to it; a single batch gets the whole machine
+            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
+                                                   batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
+                                                                      : (unsigned)c->sm_count * 32u);
             if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
-                cudaEvent_t a, b;
-                CK(cudaEventCreate(&a));
-                CK(cudaEventCreate(&b));
-                c->anchor_ev.push_back(a);
-                c->anchor_ev.push_back(b);
+                cudaEvent_t e0, e1;
+                CK(cudaEventCreate(&e0));
+                CK(cudaEventCreate(&e1));
+                c->anchor_ev.push_back(e0);
+                c->anchor_ev.push_back(e1);
             }
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st));
-            anchor_kernel<<<g1, ANC_THREADS, 0, c->st>>>(view, prm, d_desc.p, (uint32_t)tasks, d_sanc.p, d_tn.p);
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st_a));
+            anchor_kernel<<<g1, ANC_THREADS, 0, c->st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k]);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st));
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st_a));
             c->anchor_ev_used += 2;
-            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, (uint32_t)tasks, d_sanc.p, d_tn.p,
-                                                                         d_sres.p);
+            c->launches += 2;
+        }
+        CK(cudaEventRecord(c->ev_anc[k], c->st_a));
+        CK(cudaStreamWaitEvent(c->st_b, c->ev_anc[k], 0));
+        if (tasks) {
+            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st_b>>>(prm, tasks, b_anc[k], b_tn[k], b_res[k]);
             CK(cudaGetLastError());
             const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
-            ends_kernel<<<g3, END_THREADS, 0, c->st>>>(prm, (uint32_t)tasks, d_sanc.p, d_sres.p, d_tn.p, d_desc.p,
-                                                      c->d_cands.p, c->d_task_ncand.p);
-            c->launches += 3;
+            ends_kernel<<<g3, END_THREADS, 0, c->st_b>>>(prm, tasks, b_anc[k], b_res[k], b_tn[k], b_desc[k], b_cands[k],
+                                                        b_ncand[k]);
             CK(cudaGetLastError());
-            c->launches++;
+            c->launches += 2;
         }
-        finalize_kernel<<<(unsigned)np, FIN_THREADS, FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS, c->st>>>(
-            view, prm, d_info_s.p + p0, c->d_task_off.p, np, c->d_cands.p, c->d_task_ncand.p, d_perm.p + p0, d_out);
+        finalize_kernel<<<(unsigned)np, FIN_THREADS, FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS, c->st_b>>>(
+            view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_cands[k], b_ncand[k], d_perm.p + bt.p0, d_out);
         CK(cudaGetLastError());
         c->launches++;
-        p0 = p1;
+        CK(cudaEventRecord(c->ev_free[k], c->st_b));
     }
+    for (int k = 0; k < nbuf; k++) CK(cudaStreamWaitEvent(c->st, c->ev_free[k], 0));  // main stream continues after both
 }
 
 struct EdgeRun {
@@ -545,6 +607,15 @@ void skb_destroy(skb_ctx *ctx) {
     for (cudaEvent_t e : ctx->anchor_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
+    if (ctx->st_a) {
+        cudaStreamDestroy(ctx->st_a);
+        cudaStreamDestroy(ctx->st_b);
+        for (int k = 0; k < 2; k++) {
+            cudaEventDestroy(ctx->ev_anc[k]);
+            cudaEventDestroy(ctx->ev_free[k]);
+        }
+        cudaEventDestroy(ctx->ev_ready);
+    }
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->st) {
