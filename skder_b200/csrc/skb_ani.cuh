@@ -650,15 +650,17 @@ __global__ void edge_compact_kernel(const unsigned long long *__restrict__ pairs
     if (keep) edges[base + __popc(bal & ((1u << lane) - 1))] = e;
 }
 
-// roofline bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors
+// bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors (roofline
+// bytes), and the number of pairs that exceeded a kernel limit (reported as an error, never silently)
 __global__ void pair_sums_kernel(const PairInfo *__restrict__ info, const PairOut *__restrict__ po, int64_t n_pairs,
-                                 const uint64_t *__restrict__ g_seed_off, unsigned long long *sums /* [2] */) {
+                                 const uint64_t *__restrict__ g_seed_off, unsigned long long *sums /* [3] */) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sq = 0, an = 0;
     if (t < n_pairs) {
         const uint32_t q = info[t].q;
         sq = g_seed_off[q + 1] - g_seed_off[q];
         an = (unsigned long long)po[t].n_anchors;
+        if (po[t].overflow) atomicAdd(&sums[2], 1ull);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {

@@ -353,7 +353,12 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     if (total_tasks >= (1ull << 32)) throw CudaFail{"too many (pair, chunk) tasks in one call"};
     // Batches of pairs, double-buffered over two streams: the anchor kernel (L2-bound) of batch b+1 runs
     // while chain/ends/finalize (issue-bound) of batch b run.  <= 8 Mi tasks per batch (24 GiB of scratch).
-    const uint64_t max_tasks = std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + 5) / 6));
+    static const uint64_t want_batches = [] {
+        const char *e = std::getenv("SKB_PAIR_BATCHES");
+        return (uint64_t)(e ? std::max(1, atoi(e)) : 6);
+    }();
+    const uint64_t max_tasks =
+        std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + want_batches - 1) / want_batches));
     struct Batch { int64_t p0, p1; uint64_t base, tasks; };
     std::vector<Batch> batches;
     {
@@ -472,6 +477,7 @@ struct EdgeRun {
     int64_t n_screened = 0;
     float ms_screen = 0, ms_ani = 0;
     unsigned long long sums[2] = {0, 0};  // sum query seeds, sum anchors
+    int64_t n_overflow = 0;               // pairs beyond a kernel limit
 };
 
 // pairs on device -> ANI -> compacted edges on host
@@ -480,8 +486,8 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
     PoolRef<PairOut> d_out(c->pool["pairs_to_edges.d_out"]);
     PoolRef<skb_edge> d_edges(c->pool["pairs_to_edges.d_edges"]);
     PoolRef<unsigned long long> d_n(c->pool["pairs_to_edges.d_n"]);
-    d_n.reserve(3, 0, c->st);
-    CK(cudaMemsetAsync(d_n.p, 0, 24, c->st));
+    d_n.reserve(4, 0, c->st);
+    CK(cudaMemsetAsync(d_n.p, 0, 32, c->st));
     CK(cudaEventRecord(ev_mid, c->st));
     unsigned long long ne = 0;
     if (n_pairs > 0) {
@@ -500,12 +506,13 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
         CK(cudaGetLastError());
         c->launches++;
     }
-    unsigned long long h3[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(h3, d_n.p, 24, cudaMemcpyDeviceToHost, c->st));
+    unsigned long long h3[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h3, d_n.p, 32, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     ne = h3[0];
     run.sums[0] = h3[1];
     run.sums[1] = h3[2];
+    run.n_overflow = (int64_t)h3[3];
     c->last_ms_anchor = 0;
     c->last_anchor_launches = c->anchor_ev_used / 2;
     for (int i = 0; i + 1 < c->anchor_ev_used; i += 2) {
@@ -522,6 +529,10 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
 }
 
 int emit_edges(skb_ctx *c, EdgeRun &run, skb_edge **edges, int64_t *n_edges) {
+    if (run.n_overflow)
+        return fail(c, SKB_ELIMIT, std::to_string(run.n_overflow) +
+                                       " pair(s) exceed the pair-stage limits (more than 4096 chunks in the query genome or more "
+                                       "than 1024 chains with one chain per chunk); no result is returned for this call");
     *n_edges = (int64_t)run.edges.size();
     *edges = (skb_edge *)std::malloc(std::max<size_t>(1, run.edges.size()) * sizeof(skb_edge));
     if (!*edges) return fail(c, SKB_ENOMEM, "host out of memory for edges");
