@@ -70,8 +70,10 @@ def replicate_sketches(eng, dist, torch):
     return metas
 
 
-def gather_edges(edges, dist, torch, device=None):
-    """Variable-length edge arrays of all ranks -> one array sorted by (a, b) on rank 0 (empty elsewhere).
+def gather_edges(edges, dist, torch, device=None, sort=True):
+    """Variable-length edge arrays of all ranks -> one array on rank 0 (empty elsewhere), sorted by (a, b) if
+    `sort` (each rank's part is already sorted, so rank-major order is deterministic too; skDER's consumers do
+    not depend on row order).
     Two small collectives: the counts, then one padded gather of the raw 32-byte records."""
     world, rank = dist.get_world_size(), dist.get_rank()
     if device is None:
@@ -89,6 +91,8 @@ def gather_edges(edges, dist, torch, device=None):
         return np.zeros(0, EDGE_DTYPE)
     flat = recv.cpu().numpy().view(EDGE_DTYPE).reshape(world, mx)
     out = np.concatenate([flat[r, :c] for r, c in enumerate(counts)])
+    if not sort:
+        return out
     key = (out["a"].astype(np.uint64) << np.uint64(32)) | out["b"].astype(np.uint64)
     return out[np.argsort(key, kind="stable")]
 
