@@ -622,32 +622,32 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
     }
 }
 
-// K5 -- edge compaction: keep pairs with an estimate and max(AF) >= min_af; percent units
-__global__ void edge_compact_kernel(const unsigned long long *__restrict__ pairs, const PairOut *__restrict__ po,
-                                    int64_t n_pairs, double min_af /* fraction */, skb_edge *edges,
-                                    unsigned long long *n_edges) {
+// K5 -- edge compaction: keep pairs with an estimate and max(AF) >= min_af; percent units.  Order-preserving
+// (flag -> exclusive scan -> scatter): the pair list is sorted by (a, b), so the edge list comes out sorted too.
+__device__ __forceinline__ bool edge_kept(const PairOut &o, double min_af) {
+    const double afa = o.swapped ? o.af_r : o.af_q, afb = o.swapped ? o.af_q : o.af_r;
+    return o.ani >= 0.0 && (afa >= min_af || afb >= min_af);
+}
+__global__ void edge_flag_kernel(const PairOut *__restrict__ po, int64_t n_pairs, double min_af /* fraction */,
+                                 uint32_t *__restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
+    if (t < n_pairs) flag[t] = edge_kept(po[t], min_af) ? 1u : 0u;
+}
+__global__ void edge_scatter_kernel(const unsigned long long *__restrict__ pairs, const PairOut *__restrict__ po,
+                                    int64_t n_pairs, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                    skb_edge *__restrict__ edges, unsigned long long *n_edges) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    if (t == n_pairs - 1) *n_edges = (unsigned long long)pos[t] + flag[t];
+    if (!flag[t]) return;
+    const PairOut &o = po[t];
     skb_edge e;
-    if (t < n_pairs) {
-        const PairOut &o = po[t];
-        const double afa = o.swapped ? o.af_r : o.af_q, afb = o.swapped ? o.af_q : o.af_r;
-        if (o.ani >= 0.0 && (afa >= min_af || afb >= min_af)) {
-            keep = true;
-            e.a = (uint32_t)(pairs[t] >> 32);
-            e.b = (uint32_t)(pairs[t] & 0xffffffffu);
-            e.ani = o.ani * 100.0;
-            e.af_a = afa * 100.0;
-            e.af_b = afb * 100.0;
-        }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (!bal) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(n_edges, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) edges[base + __popc(bal & ((1u << lane) - 1))] = e;
+    e.a = (uint32_t)(pairs[t] >> 32);
+    e.b = (uint32_t)(pairs[t] & 0xffffffffu);
+    e.ani = o.ani * 100.0;
+    e.af_a = (o.swapped ? o.af_r : o.af_q) * 100.0;
+    e.af_b = (o.swapped ? o.af_q : o.af_r) * 100.0;
+    edges[pos[t]] = e;
 }
 
 // bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors (roofline

@@ -494,10 +494,16 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
         d_out.reserve((size_t)n_pairs, 0, c->st);
         d_edges.reserve((size_t)n_pairs, 0, c->st);
         run_ani(c, d_pairs, n_pairs, d_out.p);
-        edge_compact_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(d_pairs, d_out.p, n_pairs,
-                                                                            min_af_pct / 100.0, d_edges.p, d_n.p);
+        PoolRef<uint32_t> d_ef(c->pool["pairs_to_edges.flag"]), d_ep(c->pool["pairs_to_edges.pos"]);
+        d_ef.reserve((size_t)n_pairs, 0, c->st);
+        d_ep.reserve((size_t)n_pairs, 0, c->st);
+        edge_flag_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(d_out.p, n_pairs, min_af_pct / 100.0, d_ef.p);
         CK(cudaGetLastError());
-        c->launches++;
+        exclusive_scan_u32(c, d_ef.p, d_ep.p, (size_t)n_pairs);
+        edge_scatter_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(d_pairs, d_out.p, n_pairs, d_ef.p, d_ep.p,
+                                                                            d_edges.p, d_n.p);
+        CK(cudaGetLastError());
+        c->launches += 2;
     }
     CK(cudaEventRecord(ev_end, c->st));
     if (n_pairs > 0) {
@@ -523,9 +529,7 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
     c->anchor_ev_used = 0;
     run.edges.resize((size_t)ne);
     if (ne) CK(cudaMemcpy(run.edges.data(), d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost));
-    std::sort(run.edges.begin(), run.edges.end(), [](const skb_edge &x, const skb_edge &y) {
-        return x.a != y.a ? x.a < y.a : x.b < y.b;
-    });
+    // rect lists are sorted by (ref, query) on the device already; nothing to do on the host
 }
 
 int emit_edges(skb_ctx *c, EdgeRun &run, skb_edge **edges, int64_t *n_edges) {
