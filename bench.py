@@ -234,11 +234,17 @@ def run_ours(args):
 
     def sketch_all():
         """host packed genomes -> replicated, indexed sketch DB on every rank"""
+        t0 = time.perf_counter()
         eng.clear()
         eng._ck(L_.skb_add_genomes(eng._h, len(views), arr), "skb_add_genomes")
+        t1 = time.perf_counter()
         if world > 1:
             multi.replicate_sketches(eng, dist, torch)
+        t2 = time.perf_counter()
         eng.index()
+        if os.environ.get("SKB_BENCH_DEBUG") == "1" and rank == 0:
+            sys.stderr.write("add %.2f ms  replicate %.2f ms  index %.2f ms\n" % (
+                (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3))
 
     def barrier():
         if world > 1:

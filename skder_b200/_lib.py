@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libskani_b200.so")
+LIB_PATH = os.environ.get("SKB_LIB") or os.path.join(HERE, "_lib", "libskani_b200.so")  # SKB_LIB: A/B builds
 
 
 class SkbError(RuntimeError):

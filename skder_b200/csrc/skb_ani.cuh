@@ -35,6 +35,7 @@ constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA 
 constexpr int MAXA = 256;                     // anchors per chunk
 constexpr int MAXP = 1024;                    // chain candidates per pair
 constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
+constexpr int ENDS_K = 8;                     // qualifying DP trees per chunk tracked inside chain_kernel
 constexpr int SLOTS = 4;                      // candidate slots per task (max_chunk_chains upper bound)
 constexpr int FIN_THREADS = 256;
 constexpr uint32_t FIN_MAX_CHUNKS = 4096;     // chunks of a query genome the finalize kernel accumulates in smem
@@ -141,12 +142,21 @@ __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, 
 // buckets, covered by the other resident warps.
 __global__ void __launch_bounds__(ANC_THREADS, 4)
 anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint32_t n_tasks,
-              uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n) {
+              uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n, uint32_t *__restrict__ next_task) {
     __shared__ uint32_t stage_all[ANC_THREADS / 32][32 * STAGE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stage = stage_all[warp];
-    const uint32_t warps_total = gridDim.x * (ANC_THREADS / 32);
-    for (uint32_t t = blockIdx.x * (ANC_THREADS / 32) + warp; t < n_tasks; t += warps_total) {
+    // Tasks are handed out in order from one counter, not strided by CTA: the grid is persistent and, next to the
+    // consumer kernels of the previous batch, its CTAs become resident at different times; a CTA that starts late
+    // must join the others on the reference tables that are in L2 NOW (tasks are reference-major), not work
+    // through a fixed share milliseconds behind them (measured: 11 ms -> 54 ms per launch with a strided loop).
+    for (;;) {
+        uint32_t t = blockIdx.x * (ANC_THREADS / 32) + warp;  // next_task == nullptr: one task per warp
+        if (next_task) {
+            if (lane == 0) t = atomicAdd(next_task, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+        }
+        if (t >= n_tasks) break;
         const TaskDesc d = desc[t];
         const int nseeds = (int)d.nseeds;
         int n = 0;
@@ -168,6 +178,7 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
         }
         if (lane == 0) task_n[t] = (uint16_t)n;
         __syncwarp();
+        if (!next_task) break;
     }
 }
 
@@ -181,7 +192,8 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
 //   F = f + anchor_score
 __global__ void __launch_bounds__(DP_THREADS, 4)
 chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uint16_t *__restrict__ task_n,
-             uint32_t *__restrict__ res_all) {
+             uint32_t *__restrict__ res_all, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
+             uint8_t *__restrict__ task_ncand, uint8_t *__restrict__ task_slow) {
     const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
     const int my_n = t < n_tasks ? (int)task_n[t] : 0;
     const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
@@ -201,6 +213,32 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     const uint64_t *ap = anc_all + (size_t)tt * MAXA;
     uint32_t *rp = res_all + (size_t)tt * MAXA;
     const unsigned band = (unsigned)prm.band_bp;
+    // chain ends, tracked on the fly: per DP tree (root) the best qualifying end as
+    //   (f << 16) | (255 - i) << 8 | root   -- max over a tree = highest score, ties lowest index.
+    // Anchors of a tree arrive mostly back to back, so the tree in progress sits in (cur_root, cur_e) and the
+    // table of finished trees is touched only when the root changes.  More than ENDS_K qualifying trees in one
+    // chunk (rare) hands the task to ends_kernel.  Valid because min_score > (min_anchors - 1) * anchor_score
+    // (checked at context creation): an end that reaches min_score has min_anchors anchors, and if the tree's
+    // best end does not qualify nothing in the tree does.
+    __shared__ uint32_t tb_s[ENDS_K][DP_THREADS];  // dynamic indexing without local memory; column per thread
+    uint32_t *const tb = &tb_s[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < ENDS_K; k++) tb[k * DP_THREADS] = 0;
+    uint32_t cur_root = 0xffffffffu, cur_e = 0;
+    bool slow = false;
+    auto flush = [&](uint32_t e) {  // kept small on purpose: it is inlined once per unrolled anchor (I-cache)
+        if (e == 0) return;
+        int k = 0;
+#pragma unroll 1
+        for (; k < ENDS_K; k++) {  // entries fill front to back and never leave: first empty-or-same-root slot
+            const uint32_t v = tb[k * DP_THREADS];
+            if (v == 0 || ((v ^ e) & 0xffu) == 0) {
+                tb[k * DP_THREADS] = v > e ? v : e;
+                break;
+            }
+        }
+        if (k == ENDS_K) slow = true;
+    };
     ulonglong2 vnext[UNR / 2];
 #pragma unroll
     for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap) + x);
@@ -242,6 +280,17 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;
             const bool live = i0 + x < my_n;
+            if (live && best >= prm.min_score && (int)(rci & 0x1ffu) >= prm.min_anchors) {
+                const uint32_t root = rci >> 9;
+                const uint32_t e = ((uint32_t)best << 16) | ((uint32_t)(MAXA - 1 - (i0 + x)) << 8) | root;
+                if (root == cur_root)
+                    cur_e = cur_e > e ? cur_e : e;
+                else {
+                    flush(cur_e);
+                    cur_root = root;
+                    cur_e = e;
+                }
+            }
             Q[me] = qi + 1;
             D[me] = Di;
             F[me] = live ? best + prm.anchor_score : -(1 << 24);
@@ -260,21 +309,76 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             RC[u] = RC[u - UNR];
         }
     }
+    // ---- the chunk's top candidates, by (score desc, q0, r0), into the task's slots
+    if (my_n == 0) return;
+    flush(cur_e);
+    if (slow) {
+        task_slow[t] = 1;
+        return;
+    }
+    uint64_t key[ENDS_K];
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < ENDS_K; k++) {
+        key[k] = ~0ull;
+        const uint32_t e = tb[k * DP_THREADS];
+        if (e) {
+            const uint64_t ar = __ldcg(ap + (e & 0xffu));
+            const uint64_t ae = __ldcg(ap + (MAXA - 1 - ((e >> 8) & 0xffu)));
+            const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+            key[k] = ((uint64_t)(8191u - (e >> 16)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
+            m++;
+        }
+    }
+    const TaskDesc d = desc[t];
+    const int n_out = m < prm.max_chunk_chains ? m : prm.max_chunk_chains;
+    for (int ord = 0; ord < n_out; ord++) {
+        int bk = 0;
+        uint64_t bkey = key[0];
+#pragma unroll
+        for (int k = 1; k < ENDS_K; k++)
+            if (key[k] < bkey) {
+                bkey = key[k];
+                bk = k;
+            }
+#pragma unroll
+        for (int k = 0; k < ENDS_K; k++)
+            if (k == bk) key[k] = ~0ull;
+        const uint32_t e = tb[bk * DP_THREADS];
+        const int iend = MAXA - 1 - (int)((e >> 8) & 0xffu);
+        const uint64_t ar = __ldcg(ap + (e & 0xffu)), ae = __ldcg(ap + iend);
+        const uint32_t x = __ldcg(rp + iend);  // written above by this thread
+        Cand c;
+        c.q0 = d.cstart + an_q(ar);
+        c.q1 = d.cstart + an_q(ae);
+        c.r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
+        c.r1 = an_r(ar) < an_r(ae) ? an_r(ae) : an_r(ar);
+        c.chunk = d.ch;
+        c.score = (uint16_t)(e >> 16);
+        c.n_anchors = (uint16_t)rs_cnt(x);
+        c.n_seeds = (uint16_t)(an_sidx(ae) - an_sidx(ar) + 1);
+        c.ordinal = (uint8_t)ord;
+        c.rev = (uint8_t)an_rev(ae);
+        c.pad = 0;
+        cands[(size_t)t * SLOTS + ord] = c;
+    }
+    if (n_out) task_ncand[t] = (uint8_t)n_out;
 }
 
-// ---- K4c: chain ends.  One warp per task: best end of every DP tree (ties: lowest index) with
+// ---- K4c: chain ends (fallback for chunks with more than ENDS_K qualifying trees).  One warp per task: best end of every DP tree (ties: lowest index) with
 // >= min_anchors / min_score; the chunk's top `max_chunk_chains` by (score, q0, r0) go to the task's
 // fixed candidate slots.
 __global__ void __launch_bounds__(END_THREADS)
 ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_all, const uint32_t *__restrict__ res_all,
-            const uint16_t *__restrict__ task_n, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
-            uint8_t *__restrict__ task_ncand) {
+            const uint16_t *__restrict__ task_n, const TaskDesc *__restrict__ desc, const uint8_t *__restrict__ task_slow,
+            Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
     __shared__ uint32_t bor_all[END_THREADS / 32][MAXA];
     __shared__ __align__(16) uint32_t lst_all[END_THREADS / 32][SLOTS * 8 + SLOTS * 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *bor = bor_all[warp];
     const uint32_t warps_total = gridDim.x * (END_THREADS / 32);
     for (uint32_t t = blockIdx.x * (END_THREADS / 32) + warp; t < n_tasks; t += warps_total) {
+        if (!task_slow[t]) continue;  // chain_kernel already wrote this task's candidates
         const int n = task_n[t];
         if (n == 0) continue;
         const uint32_t ch_k = desc[t].ch, cstart_k = desc[t].cstart;

@@ -217,8 +217,16 @@ void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int 
 }
 
 // ---- sketch a batch of packed genomes [g0, g1) of the caller's list ------------------------------
-void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1, const uint64_t *d_words,
-                  cudaEvent_t uploaded) {
+struct BatchMeta {
+    SketchBatch b;
+    uint32_t n_tiles = 0;
+    size_t n_warps = 0;
+};
+
+// Host-side layout of a batch -> device, one copy per batch (slot = position in the super-batch).  Issued for every
+// batch BEFORE the packed words are enqueued: small copies share the H2D copy engine with the 256 MB word copies,
+// and queued behind them they held every sketch kernel back until the last word copy had finished.
+BatchMeta sketch_meta(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1, const uint64_t *d_words, size_t slot) {
     const int32_t nb = g1 - g0;
     std::vector<uint64_t> word_off(nb + 1, 0), nbases(nb), ctg_start;
     std::vector<uint32_t> ctg_off(nb + 1, 0), tile_off(nb + 1, 0);
@@ -235,30 +243,45 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
         ctg_off[i + 1] = (uint32_t)ctg_start.size();
         tile_off[i + 1] = tile_off[i] + (uint32_t)std::max<uint64_t>(1, (nbases[i] + SK_TILE_BASES - 1) / SK_TILE_BASES);
     }
-    const uint32_t n_tiles = tile_off[nb];
-    const size_t n_warps = (size_t)n_tiles * SK_WARPS;
-    PoolRef<uint64_t> d_word_off(c->pool["sketch_batch.d_word_off"]), d_nbases(c->pool["sketch_batch.d_nbases"]), d_ctg_start(c->pool["sketch_batch.d_ctg_start"]);
-    PoolRef<uint32_t> d_ctg_off(c->pool["sketch_batch.d_ctg_off"]), d_tile_off(c->pool["sketch_batch.d_tile_off"]), d_cnt_s(c->pool["sketch_batch.d_cnt_s"]), d_cnt_m(c->pool["sketch_batch.d_cnt_m"]), d_off_s(c->pool["sketch_batch.d_off_s"]), d_off_m(c->pool["sketch_batch.d_off_m"]);
+    // u64 word_off[nb+1] | u64 nbases[nb] | u64 ctg_start[] | u32 ctg_off[nb+1] | u32 tile_off[nb+1]
+    const size_t o_nb = (size_t)nb + 1, o_cs = o_nb + (size_t)nb, o_co = o_cs + ctg_start.size();
+    const size_t n32 = (size_t)nb + 1, o_to = o_co + (n32 + 1) / 2;
+    std::vector<uint64_t> blob(o_to + (n32 + 1) / 2, 0);
+    std::copy(word_off.begin(), word_off.end(), blob.begin());
+    std::copy(nbases.begin(), nbases.end(), blob.begin() + o_nb);
+    std::copy(ctg_start.begin(), ctg_start.end(), blob.begin() + o_cs);
+    std::memcpy(blob.data() + o_co, ctg_off.data(), n32 * 4);
+    std::memcpy(blob.data() + o_to, tile_off.data(), n32 * 4);
+    PoolRef<uint64_t> d_meta(c->pool["sketch_meta." + std::to_string(slot)]);
+    d_meta.upload(blob, c->st);
+    BatchMeta m;
+    m.n_tiles = tile_off[nb];
+    m.n_warps = (size_t)m.n_tiles * SK_WARPS;
+    m.b.packed = d_words;
+    m.b.g_word_off = d_meta.p;
+    m.b.g_nbases = d_meta.p + o_nb;
+    m.b.ctg_start = d_meta.p + o_cs;
+    m.b.g_ctg_off = reinterpret_cast<const uint32_t *>(d_meta.p + o_co);
+    m.b.tile_off = reinterpret_cast<const uint32_t *>(d_meta.p + o_to);
+    m.b.n = nb;
+    m.b.first_gid = 0;  // set when the batch runs
+    return m;
+}
+
+void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t g1, const BatchMeta &meta,
+                  cudaEvent_t uploaded) {
+    const int32_t nb = g1 - g0;
+    const uint32_t n_tiles = meta.n_tiles;
+    const size_t n_warps = meta.n_warps;
+    PoolRef<uint32_t> d_cnt_s(c->pool["sketch_batch.d_cnt_s"]), d_cnt_m(c->pool["sketch_batch.d_cnt_m"]), d_off_s(c->pool["sketch_batch.d_off_s"]), d_off_m(c->pool["sketch_batch.d_off_m"]);
     CK(cudaStreamWaitEvent(c->st, uploaded, 0));  // the batch's words were enqueued on the copy stream
-    d_word_off.upload(word_off, c->st);
-    d_nbases.upload(nbases, c->st);
-    d_ctg_start.upload(ctg_start, c->st);
-    d_ctg_off.upload(ctg_off, c->st);
-    d_tile_off.upload(tile_off, c->st);
     d_cnt_s.reserve(n_warps + 1, 0, c->st);
     d_cnt_m.reserve(n_warps + 1, 0, c->st);
     d_off_s.reserve(n_warps + 1, 0, c->st);
     d_off_m.reserve(n_warps + 1, 0, c->st);
     CK(cudaMemsetAsync(d_cnt_s.p + n_warps, 0, 4, c->st));
     CK(cudaMemsetAsync(d_cnt_m.p + n_warps, 0, 4, c->st));
-    SketchBatch b;
-    b.packed = d_words;
-    b.g_word_off = d_word_off.p;
-    b.g_nbases = d_nbases.p;
-    b.g_ctg_off = d_ctg_off.p;
-    b.ctg_start = d_ctg_start.p;
-    b.tile_off = d_tile_off.p;
-    b.n = nb;
+    SketchBatch b = meta.b;
     b.first_gid = (uint32_t)c->n();
     PoolRef<ulonglong2> d_masks(c->pool["sketch_batch.d_masks"]);
     d_masks.reserve(n_warps * 32, 0, c->st);
@@ -273,7 +296,7 @@ void sketch_batch(skb_ctx *c, const skb_packed *const *gen, int32_t g0, int32_t 
     uint32_t tot_m = 0;
     PoolRef<uint32_t> d_goff(c->pool["sketch_batch.d_goff"]);
     d_goff.reserve((size_t)nb + 1, 0, c->st);
-    gather_strided_kernel<<<nblk((uint64_t)nb + 1, 256), 256, 0, c->st>>>(d_off_s.p, d_tile_off.p, SK_WARPS, nb + 1, d_goff.p);
+    gather_strided_kernel<<<nblk((uint64_t)nb + 1, 256), 256, 0, c->st>>>(d_off_s.p, b.tile_off, SK_WARPS, nb + 1, d_goff.p);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpyAsync(h_off_s.data(), d_goff.p, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, c->st));
@@ -312,6 +335,10 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     if (!c->ani_attr_set) {
         CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS)));
+        if (const char *e = std::getenv("SKB_FIN_CARVEOUT"))
+            CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        if (const char *e = std::getenv("SKB_ANC_CARVEOUT"))
+            CK(cudaFuncSetAttribute(anchor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         c->ani_attr_set = true;
     }
     const DbView view = c->view();
@@ -351,15 +378,15 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     uint64_t total_tasks = 0;
     for (uint32_t v : h_nch) total_tasks += v;
     if (total_tasks >= (1ull << 32)) throw CudaFail{"too many (pair, chunk) tasks in one call"};
-    // Batches of pairs, double-buffered over two streams: the anchor kernel (L2-bound) of batch b+1 runs
-    // while chain/ends/finalize (issue-bound) of batch b run.  <= 8 Mi tasks per batch (24 GiB of scratch).
+    // Batches of pairs bound the scratch (<= 8 Mi tasks per batch, 24 GiB) and keep a batch's reference tables and
+    // candidates warm in L2 between its kernels; two buffer sets so that SKB_OVERLAP_STREAMS can pipeline them.
     static const uint64_t want_batches = [] {
         const char *e = std::getenv("SKB_PAIR_BATCHES");
         return (uint64_t)(e ? std::max(1, atoi(e)) : 6);
     }();
     const uint64_t max_tasks =
         std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + want_batches - 1) / want_batches));
-    struct Batch { int64_t p0, p1; uint64_t base, tasks; };
+    struct Batch { int64_t p0, p1; uint64_t base, tasks; uint32_t max_nch; };
     std::vector<Batch> batches;
     {
         int64_t p0 = 0;
@@ -367,8 +394,12 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         while (p0 < n_pairs) {
             uint64_t tasks = 0;
             int64_t p1 = p0;
-            while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) tasks += h_nch[(size_t)p1++];
-            batches.push_back({p0, p1, base, tasks});
+            uint32_t max_nch = 0;
+            while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) {
+                max_nch = std::max(max_nch, h_nch[(size_t)p1]);
+                tasks += h_nch[(size_t)p1++];
+            }
+            batches.push_back({p0, p1, base, tasks, max_nch});
             base += tasks;
             p0 = p1;
         }
@@ -386,15 +417,22 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         }
         CK(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     }
-    const char *names[2][6] = {{"ani0.anc", "ani0.res", "ani0.tn", "ani0.desc", "ani0.cands", "ani0.ncand"},
-                               {"ani1.anc", "ani1.res", "ani1.tn", "ani1.desc", "ani1.cands", "ani1.ncand"}};
-    const int nbuf = batches.size() > 1 ? 2 : 1;
+    const char *names[2][8] = {
+        {"ani0.anc", "ani0.res", "ani0.tn", "ani0.desc", "ani0.cands", "ani0.ncand", "ani0.slow", "ani0.next"},
+        {"ani1.anc", "ani1.res", "ani1.tn", "ani1.desc", "ani1.cands", "ani1.ncand", "ani1.slow", "ani1.next"}};
+    // One in-order stream by default.  SKB_OVERLAP_STREAMS=1 runs the anchor kernel of batch b+1 (low priority) next to
+    // chain/finalize of batch b (high priority) on two streams; measured on B200 this is never faster (the consumers
+    // fill the machine, and an anchor kernel that starts beside finalize's large shared-memory carve-out stays slow
+    // for its whole run: 122 ms serial vs 126-143 ms overlapped on config3), so it is kept only as an experiment.
+    static const bool serial = std::getenv("SKB_OVERLAP_STREAMS") == nullptr;
+    const int nbuf = !serial && batches.size() > 1 ? 2 : 1;  // in-order execution reuses one buffer set
     uint64_t *b_anc[2];
     uint32_t *b_res[2];
     uint16_t *b_tn[2];
     TaskDesc *b_desc[2];
     Cand *b_cands[2];
-    uint8_t *b_ncand[2];
+    uint8_t *b_ncand[2], *b_slow[2];
+    uint32_t *b_next[2];  // the anchor kernel's task counter
     for (int k = 0; k < nbuf; k++) {
         PoolRef<uint64_t> r0(c->pool[names[k][0]]);
         PoolRef<uint32_t> r1(c->pool[names[k][1]]);
@@ -408,6 +446,12 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         r3.reserve((size_t)cap, 0, c->st);
         r4.reserve((size_t)cap * SLOTS, 0, c->st);
         r5.reserve((size_t)cap, 0, c->st);
+        PoolRef<uint8_t> r6(c->pool[names[k][6]]);
+        r6.reserve((size_t)cap, 0, c->st);
+        b_slow[k] = r6.p;
+        PoolRef<uint32_t> r7(c->pool[names[k][7]]);
+        r7.reserve(1, 0, c->st);
+        b_next[k] = r7.p;
         b_anc[k] = r0.p;
         b_res[k] = r1.p;
         b_tn[k] = r2.p;
@@ -419,25 +463,44 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         const char *e = std::getenv("SKB_ANCHOR_CTAS_PER_SM");
         return e ? std::max(1, atoi(e)) : 3;
     }();
+    static const bool trace = std::getenv("SKB_TRACE") != nullptr;            // diagnosis: per-kernel timeline on stderr
+    struct Span { const char *name; size_t batch; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    cudaEvent_t ev_t0 = nullptr;
+    auto mark = [&](cudaStream_t s) {
+        cudaEvent_t e = nullptr;
+        if (trace) {
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, s));
+        }
+        return e;
+    };
+    if (trace) ev_t0 = mark(c->st);
+    const cudaStream_t st_a = serial ? c->st : c->st_a, st_b = serial ? c->st : c->st_b;
     CK(cudaEventRecord(c->ev_ready, c->st));
-    CK(cudaStreamWaitEvent(c->st_a, c->ev_ready, 0));
-    CK(cudaStreamWaitEvent(c->st_b, c->ev_ready, 0));
+    CK(cudaStreamWaitEvent(st_a, c->ev_ready, 0));
+    CK(cudaStreamWaitEvent(st_b, c->ev_ready, 0));
     for (size_t bi = 0; bi < batches.size(); bi++) {
         const Batch &bt = batches[bi];
-        const int k = (int)(bi & 1);
+        const int k = nbuf == 2 ? (int)(bi & 1) : 0;
         const int64_t np = bt.p1 - bt.p0;
         const uint32_t tasks = (uint32_t)bt.tasks, base = (uint32_t)bt.base;
-        if (bi >= 2) CK(cudaStreamWaitEvent(c->st_a, c->ev_free[k], 0));  // buffer k is free again
+        if (nbuf == 2 && bi >= 2) CK(cudaStreamWaitEvent(st_a, c->ev_free[k], 0));  // buffer k is free again
         if (tasks) {
-            CK(cudaMemsetAsync(b_ncand[k], 0, (size_t)tasks, c->st_a));
-            task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st_a>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base,
+            CK(cudaMemsetAsync(b_ncand[k], 0, (size_t)tasks, st_a));
+            CK(cudaMemsetAsync(b_slow[k], 0, (size_t)tasks, st_a));
+            CK(cudaMemsetAsync(b_next[k], 0, 4, st_a));
+            task_setup_kernel<<<nblk(tasks, 256), 256, 0, st_a>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base,
                                                                      np, tasks, b_desc[k]);
             CK(cudaGetLastError());
             // pipelined: a persistent grid of `anchor_ctas_per_sm` CTAs per SM, so the consumer kernels of the previous
             // batch find free registers next to it; a single batch gets the whole machine
-            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
-                                                   batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
-                                                                      : (unsigned)c->sm_count * 32u);
+            static const bool one_shot = std::getenv("SKB_ANCHOR_ONE_SHOT") != nullptr;  // a task per warp, no loop
+            const unsigned g1 =
+                one_shot ? nblk(tasks, ANC_THREADS / 32)
+                         : std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
+                                              !serial && batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
+                                                                            : (unsigned)c->sm_count * 32u);
             if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0));
@@ -445,31 +508,53 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                 c->anchor_ev.push_back(e0);
                 c->anchor_ev.push_back(e1);
             }
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st_a));
-            anchor_kernel<<<g1, ANC_THREADS, 0, c->st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k]);
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], st_a));
+            cudaEvent_t t0 = mark(st_a);
+            anchor_kernel<<<g1, ANC_THREADS, 0, st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k],
+                                                        one_shot ? nullptr : b_next[k]);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st_a));
+            if (trace) spans.push_back({"anchor", bi, t0, mark(st_a)});
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], st_a));
             c->anchor_ev_used += 2;
             c->launches += 2;
         }
-        CK(cudaEventRecord(c->ev_anc[k], c->st_a));
-        CK(cudaStreamWaitEvent(c->st_b, c->ev_anc[k], 0));
+        CK(cudaEventRecord(c->ev_anc[k], st_a));
+        CK(cudaStreamWaitEvent(st_b, c->ev_anc[k], 0));
         if (tasks) {
-            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st_b>>>(prm, tasks, b_anc[k], b_tn[k], b_res[k]);
+            cudaEvent_t t0 = mark(st_b);
+            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, st_b>>>(prm, tasks, b_anc[k], b_tn[k], b_res[k], b_desc[k],
+                                                                           b_cands[k], b_ncand[k], b_slow[k]);
             CK(cudaGetLastError());
+            if (trace) spans.push_back({"chain", bi, t0, mark(st_b)});
             const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
-            ends_kernel<<<g3, END_THREADS, 0, c->st_b>>>(prm, tasks, b_anc[k], b_res[k], b_tn[k], b_desc[k], b_cands[k],
-                                                        b_ncand[k]);
+            ends_kernel<<<g3, END_THREADS, 0, st_b>>>(prm, tasks, b_anc[k], b_res[k], b_tn[k], b_desc[k], b_slow[k],
+                                                        b_cands[k], b_ncand[k]);
             CK(cudaGetLastError());
             c->launches += 2;
         }
-        finalize_kernel<<<(unsigned)np, FIN_THREADS, FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS, c->st_b>>>(
+        cudaEvent_t tf = mark(st_b);
+        // per-chunk accumulators sized for this batch's longest query (more CTAs per SM, more L1 left for neighbours)
+        const size_t fin_smem = FIN_SMEM_FIXED + 8 * (size_t)std::min<uint32_t>(bt.max_nch, FIN_MAX_CHUNKS);
+        finalize_kernel<<<(unsigned)np, FIN_THREADS, fin_smem, st_b>>>(
             view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_cands[k], b_ncand[k], d_perm.p + bt.p0, d_out);
         CK(cudaGetLastError());
+        if (trace) spans.push_back({"finalize", bi, tf, mark(st_b)});
         c->launches++;
-        CK(cudaEventRecord(c->ev_free[k], c->st_b));
+        CK(cudaEventRecord(c->ev_free[k], st_b));
     }
     for (int k = 0; k < nbuf; k++) CK(cudaStreamWaitEvent(c->st, c->ev_free[k], 0));  // main stream continues after both
+    if (trace) {
+        CK(cudaStreamSynchronize(c->st));
+        for (const Span &sp : spans) {
+            float a = 0, b = 0;
+            CK(cudaEventElapsedTime(&a, ev_t0, sp.e0));
+            CK(cudaEventElapsedTime(&b, ev_t0, sp.e1));
+            fprintf(stderr, "[skb trace] batch %zu %-8s %8.2f -> %8.2f ms (%.2f)\n", sp.batch, sp.name, a, b, b - a);
+            cudaEventDestroy(sp.e0);
+            cudaEventDestroy(sp.e1);
+        }
+        cudaEventDestroy(ev_t0);
+    }
 }
 
 struct EdgeRun {
@@ -592,7 +677,8 @@ int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
     const skb_params &p = c->prm;
     if (p.max_mult < 1 || p.max_mult > STAGE || (p.max_mult & (p.max_mult - 1)) || p.max_chunk_chains < 1 ||
         p.max_chunk_chains > SLOTS || p.band_bp >= (int32_t)CONTIG_PAD || p.band_bp < 1 || p.chunk_len < 64 ||
-        p.chunk_len > 32767 || p.anchor_score < 1 || p.anchor_score > 20 || p.ovl_den < 1) {
+        p.chunk_len > 32767 || p.anchor_score < 1 || p.anchor_score > 20 || p.ovl_den < 1 || p.min_anchors < 1 ||
+        p.min_score <= (p.min_anchors - 1) * p.anchor_score) {
         g_create_error = "parameter outside the range the kernels support";
         delete c;
         return SKB_EINVAL;
@@ -705,7 +791,7 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
                 return fail(ctx, SKB_ELIMIT, "genome too large for 31-bit padded coordinates");
         }
         // batches of <= 1 Gi bases (per-batch seed/marker totals stay far below 2^32), grouped into
-        // super-batches of <= 8 whose H2D copies are all enqueued up front on a second stream: batch i+1
+        // super-batches of <= 32 (8 GiB of packed words) whose H2D copies are all enqueued up front on a second stream: batch i+1
         // uploads while batch i is being sketched.
         ctx->add_calls.push_back({ctx->n(), ctx->n_mkeys});
         if (!ctx->st_copy) CK(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
@@ -715,7 +801,7 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
             std::vector<int32_t> cut{g0};
             std::vector<uint64_t> woff{0};
             int32_t g = g0;
-            while (g < n && cut.size() <= 8) {
+            while (g < n && cut.size() <= 32) {
                 uint64_t bases = 0, words = 0;
                 int32_t g1 = g;
                 while (g1 < n && (g1 == g || bases + (uint64_t)genomes[g1]->n_bases <= (1ull << 30))) {
@@ -735,6 +821,19 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
                 CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->up_ev.push_back(e);
             }
+            static const bool trace = std::getenv("SKB_TRACE") != nullptr;  // diagnosis: upload/sketch timeline on stderr
+            std::vector<cudaEvent_t> tev;
+            auto mark = [&](cudaStream_t s) {
+                if (!trace) return;
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                CK(cudaEventRecord(e, s));
+                tev.push_back(e);
+            };
+            std::vector<BatchMeta> metas;
+            for (size_t bi = 0; bi < nbatch; bi++)
+                metas.push_back(sketch_meta(ctx, genomes, cut[bi], cut[bi + 1], d_packed.p + woff[bi], bi));
+            mark(ctx->st_copy);
             for (size_t bi = 0; bi < nbatch; bi++) {
                 uint64_t w = woff[bi];
                 for (int32_t i = cut[bi]; i < cut[bi + 1];) {  // genomes adjacent in host memory go up as one copy
@@ -747,9 +846,22 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
                     i = j;
                 }
                 CK(cudaEventRecord(ctx->up_ev[bi], ctx->st_copy));
+                mark(ctx->st_copy);
             }
-            for (size_t bi = 0; bi < nbatch; bi++)
-                sketch_batch(ctx, genomes, cut[bi], cut[bi + 1], d_packed.p + woff[bi], ctx->up_ev[bi]);
+            for (size_t bi = 0; bi < nbatch; bi++) {
+                sketch_batch(ctx, genomes, cut[bi], cut[bi + 1], metas[bi], ctx->up_ev[bi]);
+                mark(ctx->st);
+            }
+            if (trace) {
+                CK(cudaDeviceSynchronize());
+                for (size_t i = 1; i < tev.size(); i++) {
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, tev[0], tev[i]));
+                    fprintf(stderr, "[skb trace] add %s %zu done at %8.2f ms\n", i <= nbatch ? "copy  " : "sketch",
+                            i <= nbatch ? i - 1 : i - 1 - nbatch, ms);
+                }
+                for (cudaEvent_t e : tev) cudaEventDestroy(e);
+            }
             g0 = cut.back();
         }
         return SKB_OK;

@@ -356,3 +356,32 @@ def test_engine_search_and_daemon(genomes7, oracle, built_lib, tmp_path, monkeyp
         assert daemon.request(str(db), 0, {"op": "ping"}, timeout=5.0)["n"] == 7  # one server answered all three
     finally:
         daemon.request(str(db), 0, {"op": "stop"}, timeout=5.0)
+
+
+def test_many_chains_in_one_chunk(oracle, built_lib):
+    """A query chunk stitched from 14 distant reference segments: more qualifying DP trees than chain_kernel tracks
+    in registers (fallback to ends_kernel) and more chains than slots per chunk (top-4 selection); plus a
+    tandem-duplicated reference (several hits per seed: staging, sort by reference position, multiplicity cap)."""
+    from skder_b200 import engine
+
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.integers(0, 4, 400_000)]
+    order = rng.permutation(14)
+    query = np.concatenate([ref[20_000 * (k + 1): 20_000 * (k + 1) + 1300] for k in order] + [acgt[rng.integers(0, 4, 30_000)]])
+    unit = acgt[rng.integers(0, 4, 6_000)]
+    tandem = np.concatenate([unit] * 5 + [acgt[rng.integers(0, 4, 50_000)]])  # every k-mer of `unit` 5x
+    tandem_q = np.concatenate([acgt[rng.integers(0, 4, 3_000)], unit, acgt[rng.integers(0, 4, 3_000)]])
+    sets = [[ref.tobytes()], [query.tobytes()], [tandem.tobytes()], [tandem_q.tobytes()]]
+    sk = [oracle.Sketch.from_contigs(c) for c in sets]
+    with engine.Engine(0) as e:
+        e.add([engine.pack_contigs(c) for c in sets])
+        e.index()
+        det = e.pairs_detail([0, 2], [1, 3])
+        for (i, j), d in zip([(0, 1), (2, 3)], det):
+            r = oracle.pair(sk[i], sk[j])
+            assert (d.n_chains, d.n_anchors, d.n_seeds, d.span_q, d.span_r, d.swapped) == (
+                r.n_chains, r.n_anchors_total, r.n_seeds_total, r.span_q, r.span_r, r.swapped), (i, j)
+            assert abs(d.ani - r.ani) < 1e-12 and abs(d.af_a - r.af_a) < 1e-15
+        assert det[0].n_chains == 4  # 14 chains in the first query chunk, 4 slots
+        assert det[1].n_chains >= 1 and det[1].n_anchors > 0
