@@ -42,6 +42,12 @@ __device__ __forceinline__ uint64_t rev2_42(uint64_t x) {
     return y >> (64 - 2 * K_MARKER);
 }
 
+// reverse the order of the 16 two-bit groups of a 32-bit word
+__device__ __forceinline__ uint32_t rev2_32(uint32_t x) {
+    const uint32_t y = __brev(x);
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(SK_THREADS)
 sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__restrict__ warp_marker_cnt,
@@ -93,38 +99,65 @@ sketch_kernel(SketchBatch b, uint32_t *__restrict__ warp_seed_cnt, uint32_t *__r
         ci0 = l2;
     }
     if (!EMIT && p0 < nb) {
-        int ci = ci0;
-        uint64_t cstart = cs[ci];
-        uint64_t cnext = (ci + 1 < nc) ? cs[ci + 1] : nb;
-        // warm-up: the 20 bases before p0 (bases 12..31 of the previous word)
-        uint64_t f = 0, r = 0;
+        // The 21-mer ending at lane-local base j is a 42-bit window of the lane's 192-bit string (prevw, v.x, v.y)
+        // at bit 24 + 2j: complemented it IS the rolling reverse-complement value; the rolling forward value is the
+        // same window with its base order reversed, i.e. a window of the base-reversed string at bit 126 - 2j.
+        // So nothing rolls: per position two funnel-shift extractions with compile-time shifts (16 positions
+        // unrolled, the 32-bit words rotate between blocks), 32-bit arithmetic for the 30-bit seed, and no
+        // per-position contig bookkeeping -- every position is hashed and the invalid ones (past the genome end,
+        // or within 20 bases after a contig start) are cleared from the masks afterwards.
+        uint32_t a0 = (uint32_t)prevw, a1 = (uint32_t)(prevw >> 32), a2 = (uint32_t)v.x, a3 = (uint32_t)(v.x >> 32),
+                 a4 = (uint32_t)v.y, a5 = (uint32_t)(v.y >> 32);
+        uint32_t b0 = rev2_32(a5), b1 = rev2_32(a4), b2 = rev2_32(a3), b3 = rev2_32(a2), b4 = rev2_32(a1), b5 = rev2_32(a0);
+#pragma unroll 1
+        for (int jb = 0; jb < SK_LANE_BASES / 16; jb++) {
+            uint32_t sm16 = 0, mm16 = 0;
 #pragma unroll
-        for (int j = 32 - (K_MARKER - 1); j < 32; j++) {
-            uint64_t c = (prevw >> (2 * j)) & 3;
-            f = ((f << 2) | c) & MASK_MARKER;
-            r = (r >> 2) | ((3 - c) << (2 * (K_MARKER - 1)));
-        }
-#pragma unroll 4
-        for (int j = 0; j < SK_LANE_BASES; j++) {
-            const uint64_t p = p0 + j;
-            if (p >= nb) break;
-            while (p >= cnext) {
-                ci++;
-                cstart = cnext;
-                cnext = (ci + 1 < nc) ? cs[ci + 1] : nb;
-            }
-            const uint64_t w = (j < 32) ? v.x : v.y;
-            const uint64_t c = (w >> (2 * (j & 31))) & 3;
-            f = ((f << 2) | c) & MASK_MARKER;
-            r = (r >> 2) | ((3 - c) << (2 * (K_MARKER - 1)));
-            if (p - cstart >= (uint64_t)(K_MARKER - 1)) {
-                const uint64_t fs = f & MASK_SEED, rs = r >> (2 * (K_MARKER - K_SEED));
-                const uint64_t cseed = fs < rs ? fs : rs;
-                if (mm_hash64(cseed) < THR_SEED) seed_mask |= 1ull << j;
+            for (int u = 0; u < 16; u++) {
+                // reverse-complement window: ~(a >> (24 + 2u)), 42 bits
+                constexpr int HI10 = (1 << (2 * K_MARKER - 32)) - 1;
+                const int sh = 24 + 2 * u;
+                uint32_t xlo, xhi;
+                if (sh < 32) {
+                    xlo = __funnelshift_r(a0, a1, sh);
+                    xhi = __funnelshift_r(a1, a2, sh);
+                } else {
+                    xlo = __funnelshift_r(a1, a2, sh - 32);
+                    xhi = a2 >> (sh - 32);
+                }
+                const uint32_t rlo = ~xlo, rhi = ~xhi & HI10;
+                // forward window: b >> (30 - 2u) with b0..b2 = words 3-jb .. 5-jb of the reversed string
+                const int sf = 30 - 2 * u;
+                const uint32_t flo = __funnelshift_r(b3, b4, sf);
+                const uint32_t fhi = __funnelshift_r(b4, b5, sf) & HI10;
+                // seed: last 15 bases = low 30 bits of f, top 30 bits of r
+                const uint32_t fs = flo & (uint32_t)MASK_SEED;
+                const uint32_t rs = __funnelshift_r(rlo, rhi, 2 * (K_MARKER - K_SEED));
+                const uint32_t cseed = fs < rs ? fs : rs;
+                if (mm_hash64((uint64_t)cseed) < THR_SEED) sm16 |= 1u << u;
+                const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
                 const uint64_t cm = f < r ? f : r;
-                if (mm_hash64(cm) < THR_MARKER) marker_mask |= 1ull << j;
+                if (mm_hash64(cm) < THR_MARKER) mm16 |= 1u << u;
             }
+            seed_mask |= (uint64_t)sm16 << (16 * jb);
+            marker_mask |= (uint64_t)mm16 << (16 * jb);
+            a0 = a1, a1 = a2, a2 = a3, a3 = a4, a4 = a5, a5 = 0;
+            b5 = b4, b4 = b3, b3 = b2, b2 = b1, b1 = b0, b0 = 0;
         }
+        // valid positions: inside the genome, and a full 21-mer inside one contig
+        const uint64_t left = nb - p0;
+        uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
+        for (int k = ci0; k < nc; k++) {
+            const int64_t lo = (int64_t)cs[k] - (int64_t)p0;  // contig start relative to the lane
+            if (lo >= SK_LANE_BASES) break;
+            const int64_t hi = lo + (K_MARKER - 1);
+            if (hi <= 0) continue;
+            const int l = lo < 0 ? 0 : (int)lo, h = hi > SK_LANE_BASES ? SK_LANE_BASES : (int)hi;
+            const uint64_t span = (h - l) >= 64 ? ~0ull : ((1ull << (h - l)) - 1);
+            valid &= ~(span << l);
+        }
+        seed_mask &= valid;
+        marker_mask &= valid;
     }
     const int ns = __popcll(seed_mask), nm = __popcll(marker_mask);
     if (!EMIT) {
