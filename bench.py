@@ -255,10 +255,10 @@ def run_ours(args):
 
     def triangle():
         t0 = time.perf_counter()
-        edges, st = eng.triangle(GREEDY_SCREEN, GREEDY_MIN_AF, part=rank, n_parts=world)
+        edges, st = eng.triangle(GREEDY_SCREEN, GREEDY_MIN_AF, part=rank, n_parts=world, to_host=world == 1)
         t1 = time.perf_counter()
         if world > 1:
-            edges = multi.gather_edges(edges, dist, torch, sort=False)
+            edges = multi.gather_device_edges(eng, dist, torch, sort=False)
         if dbg and rank == 0:
             sys.stderr.write("triangle %.2f ms (screen %.2f ani %.2f) gather %.2f ms\n" % (
                 (t1 - t0) * 1e3, st.ms_screen, st.ms_ani, (time.perf_counter() - t1) * 1e3))

@@ -134,8 +134,8 @@ typedef struct {
 } skb_stats;
 
 /* `skani triangle -l list --min-af A -E -s S` (skder.py:16-18): all pairs a<b of the DB whose
- * row a belongs to partition `part` of `n_parts` (rows are dealt round-robin; use 0,1 for the whole
- * triangle).  screen_pct = skani -s (percent; <=0 disables), min_af_pct = skani --min-af. */
+ * row a belongs to partition `part` of `n_parts` (rows are dealt in zig-zag order 0..P-1,P-1..0,... so that all partitions
+ * hold the same number of pairs; use 0,1 for the whole triangle).  screen_pct = skani -s (percent; <=0 disables), min_af_pct = skani --min-af. */
 int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t part, int32_t n_parts,
                  skb_edge **edges, int64_t *n_edges, skb_stats *stats);
 
@@ -167,6 +167,12 @@ int skb_sketch_view_get(skb_ctx *ctx, skb_sketch_view *view);
 int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_seeds, int64_t n_seeds,
                         const uint64_t *dev_marker_keys, int64_t n_marker_keys, const uint64_t *host_seed_off,
                         const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len);
+
+/* Device copy of the edge list produced by the last skb_triangle / skb_rect call on this context (same order
+ * as the host copy; valid until the next call on the context).  skb_triangle accepts edges == NULL: the result
+ * then stays on the device only -- what a multi-GPU caller wants, which gathers the per-rank lists over NCCL
+ * (skder_b200/multi.py) instead of bouncing them through host memory. */
+int skb_device_edges(skb_ctx *ctx, const skb_edge **dev_edges, int64_t *n_edges);
 
 void skb_free(void *p);
 

@@ -105,6 +105,7 @@ SYMBOLS = [
     "skb_sketch_sizes", "skb_get_seeds", "skb_get_markers", "skb_db_save", "skb_db_load", "skb_triangle",
     "skb_rect", "skb_pairs_detail", "skb_shared_markers", "skb_sketch_view_get", "skb_import_sketches",
     "skb_free", "skb_launch_count", "skb_stream", "skb_clear", "skb_timer_start", "skb_timer_stop", "skb_index_append", "skb_pop_last_add",
+    "skb_device_edges",
 ]
 
 _lib = None

@@ -96,6 +96,8 @@ struct skb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     bool ani_attr_set = false;
+    const skb_edge *last_dev_edges = nullptr;  // device copy of the last triangle/rect result (skb_device_edges)
+    int64_t last_n_edges = 0;
     std::vector<cudaEvent_t> anchor_ev;  // start/stop pairs around the anchor kernel launches of the current call
     int anchor_ev_used = 0;
     float last_ms_anchor = 0;
@@ -558,7 +560,9 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
 }
 
 struct EdgeRun {
-    std::vector<skb_edge> edges;
+    bool to_host = true;        // false: the caller only wants the device copy (skb_device_edges)
+    skb_edge *host = nullptr;   // malloc'ed result, handed to the caller by emit_edges
+    int64_t n_edges = 0;
     int64_t n_screened = 0;
     float ms_screen = 0, ms_ani = 0;
     unsigned long long sums[2] = {0, 0};  // sum query seeds, sum anchors
@@ -612,8 +616,21 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
         c->last_ms_anchor += ms;
     }
     c->anchor_ev_used = 0;
-    run.edges.resize((size_t)ne);
-    if (ne) CK(cudaMemcpy(run.edges.data(), d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost));
+    run.n_edges = (int64_t)ne;
+    c->last_dev_edges = d_edges.p;
+    c->last_n_edges = (int64_t)ne;
+    if (run.to_host && !run.n_overflow) {
+        run.host = (skb_edge *)std::malloc(std::max<size_t>(1, (size_t)ne) * sizeof(skb_edge));
+        if (!run.host) throw CudaFail{"host out of memory for edges"};
+        if (ne) {
+            const cudaError_t e = cudaMemcpy(run.host, d_edges.p, (size_t)ne * sizeof(skb_edge), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                std::free(run.host);
+                run.host = nullptr;
+                CK(e);
+            }
+        }
+    }
     // rect lists are sorted by (ref, query) on the device already; nothing to do on the host
 }
 
@@ -622,10 +639,8 @@ int emit_edges(skb_ctx *c, EdgeRun &run, skb_edge **edges, int64_t *n_edges) {
         return fail(c, SKB_ELIMIT, std::to_string(run.n_overflow) +
                                        " pair(s) exceed the pair-stage limits (more than 4096 chunks in the query genome or more "
                                        "than 1024 chains with one chain per chunk); no result is returned for this call");
-    *n_edges = (int64_t)run.edges.size();
-    *edges = (skb_edge *)std::malloc(std::max<size_t>(1, run.edges.size()) * sizeof(skb_edge));
-    if (!*edges) return fail(c, SKB_ENOMEM, "host out of memory for edges");
-    if (!run.edges.empty()) std::memcpy(*edges, run.edges.data(), run.edges.size() * sizeof(skb_edge));
+    *n_edges = run.n_edges;
+    if (edges) *edges = run.host;
     return SKB_OK;
 }
 
@@ -728,6 +743,15 @@ void skb_destroy(skb_ctx *ctx) {
 
 const char *skb_last_error(const skb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int32_t skb_n_genomes(const skb_ctx *ctx) { return ctx ? ctx->n() : 0; }
+int skb_device_edges(skb_ctx *ctx, const skb_edge **dev_edges, int64_t *n_edges) {
+    return guarded(ctx, [&]() -> int {
+        if (!dev_edges || !n_edges) return fail(ctx, SKB_EINVAL, "bad arguments");
+        *dev_edges = ctx->last_dev_edges;
+        *n_edges = ctx->last_n_edges;
+        return SKB_OK;
+    });
+}
+
 int64_t skb_launch_count(const skb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void *skb_stream(const skb_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
 void skb_free(void *p) { std::free(p); }
@@ -1162,7 +1186,7 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
                  skb_edge **edges, int64_t *n_edges, skb_stats *stats) {
     return guarded(ctx, [&]() -> int {
         skb_ctx *c = ctx;
-        if (!edges || !n_edges || n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
+        if (!n_edges || n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
         if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
         if (c->n_inv_genomes != c->n()) return fail(c, SKB_ESTATE, "query-only genomes present: triangle needs skb_index");
         const uint32_t n = (uint32_t)c->n_indexed;
@@ -1172,9 +1196,9 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
         CK(cudaEventCreate(&e1));
         CK(cudaEventCreate(&e2));
         CK(cudaEventRecord(e0, c->st));
-        const uint32_t rows_local = (n > (uint32_t)part) ? (n - 1 - (uint32_t)part) / (uint32_t)n_parts + 1 : 0;
+        const uint32_t rows_local = rows_owned(n, (uint32_t)part, (uint32_t)n_parts);
         int64_t pairs_total = 0;
-        for (uint32_t a = (uint32_t)part; a < n; a += (uint32_t)n_parts) pairs_total += n - 1 - a;
+        for (uint32_t rl = 0; rl < rows_local; rl++) pairs_total += n - 1 - row_global(rl, (uint32_t)part, (uint32_t)n_parts);
         PoolRef<uint32_t> d_cnt(c->pool["skb_triangle.d_cnt"]);
         PoolRef<unsigned long long> d_pairs(c->pool["skb_triangle.d_pairs"]), d_pairs_sorted(c->pool["skb_triangle.d_pairs_sorted"]), d_np(c->pool["skb_triangle.d_np"]);
         d_np.reserve(1, 0, c->st);
@@ -1213,6 +1237,7 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
             }
         }
         EdgeRun run;
+        run.to_host = edges != nullptr;
         run.n_screened = (int64_t)np;
         pairs_to_edges(c, d_pairs_sorted.p, (int64_t)np, min_af_pct, run, e1, e2);
         float ms01 = 0, ms12 = 0;
@@ -1224,7 +1249,7 @@ int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t par
         if (stats) {
             stats->n_pairs_total = pairs_total;
             stats->n_pairs_screened = (int64_t)np;
-            stats->n_edges = (int64_t)run.edges.size();
+            stats->n_edges = run.n_edges;
             stats->ms_screen = ms01;
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;
@@ -1320,7 +1345,7 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
         if (stats) {
             stats->n_pairs_total = (int64_t)cells;
             stats->n_pairs_screened = (int64_t)np;
-            stats->n_edges = (int64_t)run.edges.size();
+            stats->n_edges = run.n_edges;
             stats->ms_screen = ms01;
             stats->ms_ani = ms12;
             stats->ms_total = ms01 + ms12;

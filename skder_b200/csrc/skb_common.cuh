@@ -46,6 +46,22 @@ __host__ __device__ inline uint64_t mm_hash64(uint64_t key) {
     return key;
 }
 
+// Rows of the pair triangle are dealt to partitions in zig-zag order (0..P-1, P-1..0, 0..P-1, ...).  Row a holds
+// n-1-a pairs, so every two consecutive rounds give all partitions the same number of pairs (a plain round-robin
+// leaves partition 0 with 4% more pairs than partition P-1 at n = 5000, P = 4).
+__host__ __device__ inline uint32_t row_owner(uint32_t a, uint32_t P) {
+    const uint32_t m = a % (2 * P);
+    return m < P ? m : 2 * P - 1 - m;
+}
+__host__ __device__ inline uint32_t row_local(uint32_t a, uint32_t P) { return 2 * (a / (2 * P)) + (a % (2 * P) >= P ? 1u : 0u); }
+__host__ __device__ inline uint32_t row_global(uint32_t rl, uint32_t part, uint32_t P) {
+    return (rl >> 1) * 2 * P + ((rl & 1) ? 2 * P - 1 - part : part);
+}
+__host__ __device__ inline uint32_t rows_owned(uint32_t n, uint32_t part, uint32_t P) {
+    const uint32_t rem = n % (2 * P);
+    return 2 * (n / (2 * P)) + (rem > part ? 1u : 0u) + (rem > 2 * P - 1 - part ? 1u : 0u);
+}
+
 // Seed index layout: buckets of 4 slots (one 32-byte sector).  A k-mer's entries live in its home
 // bucket; a bucket that is full spills into the next one, so a lookup reads buckets until it meets
 // one with a free slot -- at load factor 0.5 that is 1.05 sectors on average, the same for every lane.

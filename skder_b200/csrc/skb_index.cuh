@@ -85,16 +85,16 @@ __global__ void strip_gid_kernel(uint64_t *keys, uint64_t n) {
 
 // K3a (triangle): every run of equal markers in the inverted index contributes +1 to each pair of
 // genomes in the run.  Thread i owns entry i and pairs it with the later entries of its run, so
-// row = smaller genome id.  Rows are dealt round-robin to partitions (row % n_parts == part).
+// row = smaller genome id.  Rows are dealt to partitions in zig-zag order (row_owner, skb_common.cuh).
 __global__ void screen_runs_kernel(const uint64_t *__restrict__ inv, uint64_t n, uint32_t *cnt, uint32_t n_genomes,
                                    int part, int n_parts) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t k = inv[i];
     const uint32_t gi = (uint32_t)(k & GID_MASK);
-    if ((int)(gi % (uint32_t)n_parts) != part) return;
+    if ((int)row_owner(gi, (uint32_t)n_parts) != part) return;
     const uint64_t m = k >> GID_BITS;
-    uint32_t *row = cnt + (size_t)(gi / (uint32_t)n_parts) * n_genomes;
+    uint32_t *row = cnt + (size_t)row_local(gi, (uint32_t)n_parts) * n_genomes;
     for (uint64_t j = i + 1; j < n; j++) {
         const uint64_t kj = inv[j];
         if ((kj >> GID_BITS) != m) break;
@@ -115,7 +115,7 @@ __global__ void screen_compact_kernel(const uint32_t *__restrict__ cnt, uint32_t
     if (t < total) {
         const uint32_t rl = (uint32_t)(t / n_genomes);
         b = (uint32_t)(t % n_genomes);
-        a = rl * (uint32_t)n_parts + (uint32_t)part;
+        a = row_global(rl, (uint32_t)part, (uint32_t)n_parts);
         if (a < n_genomes && b > a) {
             if (cutoff_scale <= 0.0)
                 pass = true;

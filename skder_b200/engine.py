@@ -211,13 +211,21 @@ class Engine:
         finally:
             self._L.skb_free(ptr)
 
-    def triangle(self, screen=80.0, min_af=15.0, part=0, n_parts=1):
+    def triangle(self, screen=80.0, min_af=15.0, part=0, n_parts=1, to_host=True):
+        """to_host=False leaves the edges on the device (see device_edges) and returns (None, stats)."""
         ptr, n, st = C.POINTER(_lib.Edge)(), C.c_int64(), _lib.Stats()
         self._ck(
-            self._L.skb_triangle(self._h, float(screen), float(min_af), part, n_parts, C.byref(ptr), C.byref(n), C.byref(st)),
+            self._L.skb_triangle(self._h, float(screen), float(min_af), part, n_parts,
+                                 C.byref(ptr) if to_host else None, C.byref(n), C.byref(st)),
             "skb_triangle",
         )
-        return self._take_edges(ptr, n), st
+        return (self._take_edges(ptr, n) if to_host else None), st
+
+    def device_edges(self):
+        """(device pointer, count) of the last triangle/rect result; valid until the next call on this engine."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._ck(self._L.skb_device_edges(self._h, C.byref(ptr), C.byref(n)), "skb_device_edges")
+        return int(ptr.value or 0), int(n.value)
 
     def rect(self, refs, queries, screen=80.0, min_af=15.0):
         refs = np.ascontiguousarray(refs, np.int32)

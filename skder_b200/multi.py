@@ -87,6 +87,10 @@ def gather_edges(edges, dist, torch, device=None, sort=True):
         send[: len(edges) * EDGE_DTYPE.itemsize].copy_(torch.from_numpy(np.ascontiguousarray(edges).view(np.uint8)))
     recv = torch.empty(world * mx * EDGE_DTYPE.itemsize, dtype=torch.uint8, device=device) if rank == 0 else None
     dist.gather(send, list(recv.chunk(world)) if rank == 0 else None, dst=0)
+    return _finish_gather(recv, counts, mx, world, rank, sort)
+
+
+def _finish_gather(recv, counts, mx, world, rank, sort):
     if rank != 0:
         return np.zeros(0, EDGE_DTYPE)
     flat = recv.cpu().numpy().view(EDGE_DTYPE).reshape(world, mx)
@@ -97,7 +101,30 @@ def gather_edges(edges, dist, torch, device=None, sort=True):
     return out[np.argsort(key, kind="stable")]
 
 
+def gather_device_edges(eng, dist, torch, sort=True):
+    """gather_edges for a result that is still on the device (Engine.triangle(to_host=False)): the per-rank lists go
+    from the library's buffer over NCCL to rank 0 and reach host memory once, there."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    device = torch.device("cuda", eng.device)
+    ptr, n = eng.device_edges()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=device))
+    counts = counts.tolist()
+    mx = max(max(counts), 1)
+    words = EDGE_DTYPE.itemsize // 8
+    send = torch.empty(mx * words, dtype=torch.int64, device=device)
+    if n:
+        send[: n * words].copy_(_dev_tensor(torch, ptr, n * words, device))
+    recv = torch.empty(world * mx * words, dtype=torch.int64, device=device) if rank == 0 else None
+    dist.gather(send, list(recv.chunk(world)) if rank == 0 else None, dst=0)
+    return _finish_gather(recv.view(torch.uint8) if rank == 0 else None, counts, mx, world, rank, sort)
+
+
 def partition_rows(n, part, n_parts):
-    """Rows of the pair triangle owned by `part` (round-robin), and how many pairs that is."""
-    rows = np.arange(part, n, n_parts)
+    """Rows of the pair triangle owned by `part`, and how many pairs that is.  Rows are dealt in zig-zag order
+    (0..P-1, P-1..0, ...) so that all parts hold the same number of pairs (row a has n-1-a); the same rule as
+    row_owner() in csrc/skb_common.cuh."""
+    a = np.arange(n)
+    m = a % (2 * n_parts)
+    rows = a[np.where(m < n_parts, m, 2 * n_parts - 1 - m) == part]
     return rows, int((n - 1 - rows).sum())

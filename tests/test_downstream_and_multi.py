@@ -140,3 +140,9 @@ def test_partition_and_gather_gloo_world2():
 
     assert n_rank0 == multi.partition_rows(23, 0, 2)[1]
     assert sum(multi.partition_rows(23, r, 3)[1] for r in range(3)) == len(want)
+    # zig-zag dealing: every row exactly once, and the parts hold (almost) the same number of pairs
+    for n, world in ((5000, 4), (5000, 8), (37, 3)):
+        parts = [multi.partition_rows(n, r, world) for r in range(world)]
+        assert sorted(np.concatenate([p[0] for p in parts]).tolist()) == list(range(n))
+        sizes = [p[1] for p in parts]
+        assert max(sizes) - min(sizes) <= 2 * world * world

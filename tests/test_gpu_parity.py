@@ -95,9 +95,17 @@ def test_triangle_screen_and_edges(eng7, ora7, oracle):
 def test_triangle_partitions_cover_triangle(eng7):
     e, _ = eng7
     full, _ = e.triangle(screen=80.0, min_af=0.0)
-    parts = [e.triangle(screen=80.0, min_af=0.0, part=p, n_parts=3)[0] for p in range(3)]
-    cat = np.sort(np.concatenate(parts), order=["a", "b"])
-    assert np.array_equal(cat, np.sort(full, order=["a", "b"]))
+    from skder_b200 import multi
+
+    for n_parts in (2, 3, 5):
+        parts = []
+        for p in range(n_parts):
+            edges, st = e.triangle(screen=0.0, min_af=0.0, part=p, n_parts=n_parts)
+            rows, npairs = multi.partition_rows(7, p, n_parts)  # the host-side statement of the same dealing rule
+            assert st.n_pairs_total == npairs and set(edges["a"].tolist()) <= set(rows.tolist())
+            parts.append(e.triangle(screen=80.0, min_af=0.0, part=p, n_parts=n_parts)[0])
+        cat = np.sort(np.concatenate(parts), order=["a", "b"])
+        assert np.array_equal(cat, np.sort(full, order=["a", "b"]))
 
 
 def test_rect_equals_triangle_values(eng7):
@@ -385,3 +393,22 @@ def test_many_chains_in_one_chunk(oracle, built_lib):
             assert abs(d.ani - r.ani) < 1e-12 and abs(d.af_a - r.af_a) < 1e-15
         assert det[0].n_chains == 4  # 14 chains in the first query chunk, 4 slots
         assert det[1].n_chains >= 1 and det[1].n_anchors > 0
+
+
+def test_device_edges_match_host_copy(eng7):
+    """skb_device_edges: the device-resident result (multi-GPU gather path) equals the host copy, with and without
+    the host copy being made."""
+    import torch
+
+    from skder_b200 import multi
+    from skder_b200.engine import EDGE_DTYPE
+
+    e, _ = eng7
+    host, st = e.triangle(screen=80.0, min_af=0.0)
+    for to_host in (True, False):
+        got, st2 = e.triangle(screen=80.0, min_af=0.0, to_host=to_host)
+        assert (got is None) == (not to_host) and st2.n_edges == len(host)
+        ptr, n = e.device_edges()
+        assert n == len(host)
+        dev = multi._dev_tensor(torch, ptr, n * (EDGE_DTYPE.itemsize // 8), torch.device("cuda", e.device))
+        assert np.array_equal(dev.cpu().numpy().view(EDGE_DTYPE), host)
