@@ -81,14 +81,17 @@ __device__ __forceinline__ Bucket2 empty_buckets() {
     B.a0 = B.a1 = B.c0 = B.c1 = make_ulonglong2(TAB_EMPTY, TAB_EMPTY);
     return B;
 }
+// One bucket = one 32-byte sector = ONE 256-bit load (LDG.E.256, sm_100).  Lookups are scattered, so every load
+// instruction costs the L1 data pipe a wavefront per lane; with two 128-bit loads per bucket that pipe was the
+// anchor kernel's limit (ncu: l1tex data-pipe wavefronts 99.6% of peak).  Buckets are 32-byte aligned (table
+// offsets are multiples of BUCKET words, the allocation is 256-byte aligned).
+__device__ __forceinline__ void ld_bucket(const uint64_t *__restrict__ p, ulonglong2 &lo, ulonglong2 &hi) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(lo.x), "=l"(lo.y), "=l"(hi.x), "=l"(hi.y) : "l"(p));
+}
 __device__ __forceinline__ Bucket2 load_buckets(const uint64_t *__restrict__ T, uint32_t b1, uint32_t b2) {
     Bucket2 B;
-    const ulonglong2 *p1 = reinterpret_cast<const ulonglong2 *>(T + (size_t)b1 * BUCKET);
-    const ulonglong2 *p2 = reinterpret_cast<const ulonglong2 *>(T + (size_t)b2 * BUCKET);
-    B.a0 = __ldg(p1);
-    B.a1 = __ldg(p1 + 1);
-    B.c0 = __ldg(p2);
-    B.c1 = __ldg(p2 + 1);
+    ld_bucket(T + (size_t)b1 * BUCKET, B.a0, B.a1);
+    ld_bucket(T + (size_t)b2 * BUCKET, B.c0, B.c1);
     return B;
 }
 __device__ __forceinline__ bool both_full(const Bucket2 &B) { return B.a1.y != TAB_EMPTY && B.c1.y != TAB_EMPTY; }
@@ -106,8 +109,8 @@ __device__ __forceinline__ int tab_count(const uint64_t *__restrict__ T, uint32_
         for (;;) {
             b = (b + 1 == nb) ? 0 : b + 1;
             if (b == b2) continue;
-            const ulonglong2 x0 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET));
-            const ulonglong2 x1 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET) + 1);
+            ulonglong2 x0, x1;
+            ld_bucket(T + (size_t)b * BUCKET, x0, x1);
             c += (seed_kmer(x0.x) == kmer) + (seed_kmer(x0.y) == kmer) + (seed_kmer(x1.x) == kmer) + (seed_kmer(x1.y) == kmer);
             if (x1.y == TAB_EMPTY || c >= cap) break;
         }
@@ -168,8 +171,8 @@ __device__ __forceinline__ int probe_one(uint64_t sd, const Bucket2 &B, const ui
             for (;;) {
                 b = (b + 1 == nb) ? 0 : b + 1;
                 if (b == b2) continue;
-                const ulonglong2 x0 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET));
-                const ulonglong2 x1 = __ldg(reinterpret_cast<const ulonglong2 *>(T + (size_t)b * BUCKET) + 1);
+                ulonglong2 x0, x1;
+                ld_bucket(T + (size_t)b * BUCKET, x0, x1);
                 const uint64_t e4[4] = {x0.x, x0.y, x1.x, x1.y};
 #pragma unroll
                 for (int x = 0; x < 4; x++)
