@@ -37,23 +37,43 @@ __device__ __forceinline__ int genome_of(const uint64_t *__restrict__ off, int n
     return lo;
 }
 
+// genome_of for a warp whose lanes hold consecutive, ascending i: lane 0 searches, the others walk on from there
+// (a warp spans 32 records, a genome ~40,000).  All 32 lanes must call.
+__device__ __forceinline__ int genome_of_warp(const uint64_t *__restrict__ off, int n, uint64_t i) {
+    const uint64_t i0 = __shfl_sync(0xffffffffu, i, 0);
+    int g = 0;
+    if ((threadIdx.x & 31) == 0) g = genome_of(off, n, i0);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    while (g + 1 < n && off[g + 1] <= i) g++;
+    return g;
+}
+
 // one thread per seed record: insert into its genome's table (64-bit CAS; no deletions ever)
 __global__ void tab_insert_kernel(const uint64_t *__restrict__ seeds, uint64_t n_seeds,
                                   const uint64_t *__restrict__ g_seed_off, int n_genomes, uint64_t *tab,
                                   const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets,
                                   uint64_t first /* records [first, n_seeds) are inserted */) {
     uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = genome_of_warp(g_seed_off, n_genomes, i < n_seeds ? i : n_seeds - 1);
     if (i >= n_seeds) return;
-    const int g = genome_of(g_seed_off, n_genomes, i);
     const uint32_t nb = g_tab_buckets[g];
     volatile unsigned long long *T = reinterpret_cast<volatile unsigned long long *>(tab + g_tab_off[g]);
     const unsigned long long rec = seeds[i] & ~2ull;
     uint32_t b1, b2;
     tab_homes(seed_kmer(rec), nb, b1, b2);
     for (;;) {
-        int o1 = 0, o2 = 0;  // occupancy: slots fill in order
-        while (o1 < (int)BUCKET && T[(size_t)b1 * BUCKET + o1] != TAB_EMPTY) o1++;
-        while (o2 < (int)BUCKET && T[(size_t)b2 * BUCKET + o2] != TAB_EMPTY) o2++;
+        // occupancy of both homes from two 256-bit reads (slots fill in order); .cg: other threads are inserting
+        unsigned long long a[BUCKET], c[BUCKET];
+        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(a[0]), "=l"(a[1]), "=l"(a[2]), "=l"(a[3]) : "l"(tab + g_tab_off[g] + (size_t)b1 * BUCKET) : "memory");
+        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3]) : "l"(tab + g_tab_off[g] + (size_t)b2 * BUCKET) : "memory");
+        int o1 = 0, o2 = 0;
+#pragma unroll
+        for (int k = 0; k < (int)BUCKET; k++) {
+            o1 += a[k] != TAB_EMPTY;
+            o2 += c[k] != TAB_EMPTY;
+        }
         if (o1 == (int)BUCKET && o2 == (int)BUCKET) break;
         const uint32_t tb = o2 < o1 ? b2 : b1;
         const int slot = o2 < o1 ? o2 : o1;
@@ -124,8 +144,8 @@ __global__ void rep_flag_kernel(uint64_t *seeds, uint64_t n_seeds, const uint64_
                                 const uint64_t *__restrict__ g_tab_off, const uint32_t *__restrict__ g_tab_buckets,
                                 int max_mult, uint64_t first) {
     uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = genome_of_warp(g_seed_off, n_genomes, i < n_seeds ? i : n_seeds - 1);
     if (i >= n_seeds) return;
-    const int g = genome_of(g_seed_off, n_genomes, i);
     const uint64_t s = seeds[i];
     const int c = tab_count(tab + g_tab_off[g], g_tab_buckets[g], seed_kmer(s), max_mult + 1);
     if (c > max_mult) seeds[i] = s | 2ull;
