@@ -151,11 +151,9 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
     // must join the others on the reference tables that are in L2 NOW (tasks are reference-major), not work
     // through a fixed share milliseconds behind them (measured: 11 ms -> 54 ms per launch with a strided loop).
     for (;;) {
-        uint32_t t = blockIdx.x * (ANC_THREADS / 32) + warp;  // next_task == nullptr: one task per warp
-        if (next_task) {
-            if (lane == 0) t = atomicAdd(next_task, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-        }
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(next_task, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const TaskDesc d = desc[t];
         const int nseeds = (int)d.nseeds;
@@ -178,7 +176,6 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
         }
         if (lane == 0) task_n[t] = (uint16_t)n;
         __syncwarp();
-        if (!next_task) break;
     }
 }
 

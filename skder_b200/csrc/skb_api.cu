@@ -337,10 +337,6 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     if (!c->ani_attr_set) {
         CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS)));
-        if (const char *e = std::getenv("SKB_FIN_CARVEOUT"))
-            CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-        if (const char *e = std::getenv("SKB_ANC_CARVEOUT"))
-            CK(cudaFuncSetAttribute(anchor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         c->ani_attr_set = true;
     }
     const DbView view = c->view();
@@ -495,14 +491,11 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             task_setup_kernel<<<nblk(tasks, 256), 256, 0, st_a>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base,
                                                                      np, tasks, b_desc[k]);
             CK(cudaGetLastError());
-            // pipelined: a persistent grid of `anchor_ctas_per_sm` CTAs per SM, so the consumer kernels of the previous
-            // batch find free registers next to it; a single batch gets the whole machine
-            static const bool one_shot = std::getenv("SKB_ANCHOR_ONE_SHOT") != nullptr;  // a task per warp, no loop
-            const unsigned g1 =
-                one_shot ? nblk(tasks, ANC_THREADS / 32)
-                         : std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
-                                              !serial && batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
-                                                                            : (unsigned)c->sm_count * 32u);
+            // a persistent grid fed by the task counter; with SKB_OVERLAP_STREAMS only `anchor_ctas_per_sm` CTAs per SM,
+            // so the consumer kernels of the previous batch find free registers next to it
+            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
+                                                   !serial && batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
+                                                                                 : (unsigned)c->sm_count * 32u);
             if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0));
@@ -512,8 +505,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             }
             CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], st_a));
             cudaEvent_t t0 = mark(st_a);
-            anchor_kernel<<<g1, ANC_THREADS, 0, st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k],
-                                                        one_shot ? nullptr : b_next[k]);
+            anchor_kernel<<<g1, ANC_THREADS, 0, st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k], b_next[k]);
             CK(cudaGetLastError());
             if (trace) spans.push_back({"anchor", bi, t0, mark(st_a)});
             CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], st_a));
