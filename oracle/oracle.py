@@ -19,7 +19,7 @@ def build(force=False):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     subprocess.check_call(
-        ["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-shared", "-fPIC", "-o", _SO, src[0], "-lz", "-lm"]
+        ["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-pthread", "-shared", "-fPIC", "-o", _SO, src[0], "-lz", "-lm"]
     )
     return _SO
 
@@ -201,6 +201,29 @@ def screen(a, b, s, params=None):
     ok = C.c_int(0)
     shared = lib().ora_screen(a.h, b.h, float(s), C.byref(p), C.byref(ok))
     return shared, bool(ok.value)
+
+
+def triangle(sketches, s, min_af, threads, params=None, want_pass=False):
+    """All-vs-all of `sketches` on host threads inside the C library (no Python per pair): inverted-index prescreen,
+    ANI/AF of the survivors.  Returns a dict: survivors, edges, t_index, t_count, t_ani (seconds) and, if want_pass,
+    the n x n uint8 decision matrix (row a, column b, a < b)."""
+    p = params or default_params()
+    n = len(sketches)
+    arr = (C.c_void_p * n)(*[sk.h for sk in sketches])
+    ne, ti, tc, ta = C.c_int64(0), C.c_double(0), C.c_double(0), C.c_double(0)
+    mat = np.zeros((n, n), np.uint8) if want_pass else None
+    f = lib().ora_triangle
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p]
+    ns = f(arr, n, float(s), float(min_af), C.byref(p), int(threads), C.byref(ne),
+           mat.ctypes.data if want_pass else None, C.byref(ti), C.byref(tc), C.byref(ta))
+    if ns < 0:
+        raise ValueError("oracle triangle: too many genomes")
+    out = {"survivors": int(ns), "edges": int(ne.value), "t_index": ti.value, "t_count": tc.value, "t_ani": ta.value}
+    if want_pass:
+        out["pass"] = mat
+    return out
 
 
 def pair(a, b, params=None, want_chains=False, max_chains=8192):

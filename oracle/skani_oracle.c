@@ -606,3 +606,169 @@ retry:
     free(cands);
     return out->ani_raw >= 0 ? 0 : 1;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * All-vs-all on host threads: bench.py's CPU arm.  ANI/AF is ora_pair above, driven from C so that
+ * the measurement holds no Python per-pair overhead.  The prescreen is done the way SURVEY.md
+ * section 8 row a4 says skani does it on the CPU -- an inverted marker -> genomes index, so its cost
+ * follows the SHARED markers, not pairs x sketch size: (marker << 22 | genome) keys are radix-sorted,
+ * every run of equal markers adds 1 to the count of each genome pair in it, and the counts are
+ * thresholded with ora_screen's rule.  The decisions are identical to calling ora_screen on every
+ * pair (tests/test_oracle_golden.py checks that).  Work is handed out by an atomic counter.
+ * ------------------------------------------------------------------------------------------- */
+#include <pthread.h>
+#include <time.h>
+
+typedef struct {
+    const ora_sketch_t *const *sk;
+    int n;
+    double screen, min_af;
+    const ora_params_t *p;
+    const uint64_t *keys;   /* sorted (marker << 22 | genome) */
+    int64_t n_keys;
+    uint32_t *cnt;          /* n*n shared-marker counts, [a*n+b] for a<b */
+    uint8_t *pass;          /* n*n */
+    const uint32_t *surv;   /* 2 ints per surviving pair */
+    int64_t n_surv;
+    int64_t next;           /* atomic work counter */
+    int64_t n_edges;        /* atomic */
+    int phase;
+} tri_job_t;
+
+#define TRI_GID_BITS 22
+#define TRI_BLOCK 4096
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* LSD radix sort of 64-bit keys, 8 bits per pass, passes over constant bytes skipped */
+static void radix_sort_u64(uint64_t *a, uint64_t *tmp, int64_t n) {
+    for (int shift = 0; shift < 64; shift += 8) {
+        int64_t h[257];
+        memset(h, 0, sizeof(h));
+        for (int64_t i = 0; i < n; i++) h[((a[i] >> shift) & 255) + 1]++;
+        int constant = 0;
+        for (int b = 0; b < 256; b++)
+            if (h[b + 1] == n) constant = 1;
+        if (constant) continue;
+        for (int b = 0; b < 256; b++) h[b + 1] += h[b];
+        for (int64_t i = 0; i < n; i++) tmp[h[(a[i] >> shift) & 255]++] = a[i];
+        memcpy(a, tmp, sizeof(uint64_t) * (size_t)n);
+    }
+}
+
+static void *tri_worker(void *arg) {
+    tri_job_t *j = (tri_job_t *)arg;
+    const uint64_t gmask = ((uint64_t)1 << TRI_GID_BITS) - 1;
+    if (j->phase == 0) { /* runs of equal markers -> pair counts; a run belongs to the block it starts in */
+        for (;;) {
+            const int64_t b0 = __atomic_fetch_add(&j->next, TRI_BLOCK, __ATOMIC_RELAXED);
+            if (b0 >= j->n_keys) break;
+            int64_t i = b0;
+            const int64_t b1 = b0 + TRI_BLOCK < j->n_keys ? b0 + TRI_BLOCK : j->n_keys;
+            while (i < b1 && i > 0 && (j->keys[i] >> TRI_GID_BITS) == (j->keys[i - 1] >> TRI_GID_BITS)) i++;
+            while (i < b1) {
+                int64_t e = i + 1;
+                while (e < j->n_keys && (j->keys[e] >> TRI_GID_BITS) == (j->keys[i] >> TRI_GID_BITS)) e++;
+                for (int64_t x = i; x < e; x++)
+                    for (int64_t y = x + 1; y < e; y++)
+                        __atomic_fetch_add(&j->cnt[(size_t)(j->keys[x] & gmask) * j->n + (size_t)(j->keys[y] & gmask)], 1u,
+                                           __ATOMIC_RELAXED);
+                i = e;
+            }
+        }
+    } else if (j->phase == 1) { /* threshold the counts, ora_screen's rule */
+        const double s21 = pow(j->screen, (double)j->p->marker_k);
+        for (;;) {
+            const int64_t a = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+            if (a >= j->n) break;
+            for (int b = (int)a + 1; b < j->n; b++) {
+                const int64_t ma = j->sk[a]->n_markers, mb = j->sk[b]->n_markers;
+                const double cutoff = s21 * (double)(ma < mb ? ma : mb);
+                j->pass[(size_t)a * j->n + b] = (j->screen <= 0.0) ? 1 : ((double)j->cnt[(size_t)a * j->n + b] > cutoff);
+            }
+        }
+    } else {
+        int64_t edges = 0;
+        for (;;) {
+            const int64_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+            if (i >= j->n_surv) break;
+            ora_pair_result_t r;
+            ora_pair(j->sk[j->surv[2 * i]], j->sk[j->surv[2 * i + 1]], j->p, &r, NULL, 0, NULL);
+            if (r.ani >= 0 && (r.af_a >= j->min_af || r.af_b >= j->min_af)) edges++;
+        }
+        __atomic_fetch_add(&j->n_edges, edges, __ATOMIC_RELAXED);
+    }
+    return NULL;
+}
+
+static void tri_run(tri_job_t *j, int threads) {
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    j->next = 0;
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, tri_worker, j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+}
+
+int64_t ora_triangle(const ora_sketch_t *const *sk, int n, double screen, double min_af, const ora_params_t *p,
+                     int threads, int64_t *n_edges, uint8_t *pass_out, double *t_index, double *t_count, double *t_ani) {
+    tri_job_t j;
+    memset(&j, 0, sizeof(j));
+    if (threads < 1) threads = 1;
+    if (n >= (1 << TRI_GID_BITS)) return -1;
+    j.sk = sk;
+    j.n = n;
+    j.screen = screen;
+    j.min_af = min_af;
+    j.p = p;
+    double t0 = now_s();
+    int64_t nk = 0;
+    for (int g = 0; g < n; g++) nk += sk[g]->n_markers;
+    uint64_t *keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(nk + 1));
+    uint64_t *tmp = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(nk + 1));
+    nk = 0;
+    for (int g = 0; g < n; g++)
+        for (int64_t i = 0; i < sk[g]->n_markers; i++) keys[nk++] = (sk[g]->markers[i] << TRI_GID_BITS) | (uint64_t)g;
+    radix_sort_u64(keys, tmp, nk);
+    free(tmp);
+    double t1 = now_s();
+    j.keys = keys;
+    j.n_keys = nk;
+    j.cnt = (uint32_t *)calloc((size_t)n * (size_t)n + 1, sizeof(uint32_t));
+    j.pass = (uint8_t *)calloc((size_t)n * (size_t)n + 1, 1);
+    j.phase = 0;
+    tri_run(&j, threads);
+    j.phase = 1;
+    tri_run(&j, threads);
+    int64_t ns = 0;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++) ns += j.pass[(size_t)a * n + b];
+    uint32_t *surv = (uint32_t *)malloc(sizeof(uint32_t) * 2 * (size_t)(ns + 1));
+    int64_t k = 0;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++)
+            if (j.pass[(size_t)a * n + b]) {
+                surv[2 * k] = (uint32_t)a;
+                surv[2 * k + 1] = (uint32_t)b;
+                k++;
+            }
+    double t2 = now_s();
+    j.surv = surv;
+    j.n_surv = ns;
+    j.phase = 2;
+    tri_run(&j, threads);
+    double t3 = now_s();
+    if (n_edges) *n_edges = j.n_edges;
+    if (pass_out) memcpy(pass_out, j.pass, (size_t)n * (size_t)n);
+    if (t_index) *t_index = t1 - t0;
+    if (t_count) *t_count = t2 - t1;
+    if (t_ani) *t_ani = t3 - t2;
+    free(surv);
+    free(j.pass);
+    free(j.cnt);
+    free(keys);
+    return ns;
+}

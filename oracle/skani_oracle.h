@@ -109,6 +109,15 @@ int64_t ora_screen(const ora_sketch_t *a, const ora_sketch_t *b, double screen, 
 int ora_pair(const ora_sketch_t *a, const ora_sketch_t *b, const ora_params_t *p,
              ora_pair_result_t *out, ora_chain_t *chains, int max_chains, int *n_chains_out);
 
+/* All pairs a<b of n sketches on `threads` host threads (bench.py's CPU arm): prescreen through an inverted marker
+ * index (same decisions as ora_screen on every pair), ANI/AF for the survivors, count the edges an
+ * `skani triangle --min-af` would print (min_af in [0,1]).  Returns the number of surviving pairs (-1: too many
+ * genomes).  pass_out (may be NULL) receives the n*n decision matrix ([a*n+b], a<b).  Wall seconds: t_index = key
+ * sort (scales with genomes), t_count = run counting + threshold (scales with shared markers, i.e. with the
+ * surviving pairs), t_ani = ANI/AF (scales with the surviving pairs). */
+int64_t ora_triangle(const ora_sketch_t *const *sk, int n, double screen, double min_af, const ora_params_t *p,
+                     int threads, int64_t *n_edges, uint8_t *pass_out, double *t_index, double *t_count, double *t_ani);
+
 /* learned-debias substitute: maps raw ANI (+features) to reported ANI */
 double ora_debias(double ani_raw);
 

@@ -159,3 +159,23 @@ def test_edge_cases(oracle):
     k_two = set((two.seeds() >> np.uint64(34)).tolist())
     k_one = set((one.seeds() >> np.uint64(34)).tolist())
     assert k_two <= k_one and len(k_one) - len(k_two) <= 2  # only windows crossing the cut disappear
+
+
+def test_threaded_triangle_matches_per_pair_calls(oracle, genomes7):
+    """bench.py's CPU arm (ora_triangle: inverted-index prescreen + ANI/AF on pthreads) makes the decisions the
+    per-pair functions make."""
+    import itertools
+
+    sk = [oracle.Sketch.from_file(p) for p in genomes7]
+    n = len(sk)
+    for s, min_af in ((0.80, 0.15), (0.9995, 0.5), (0.0, 0.0)):
+        r = oracle.triangle(sk, s, min_af, threads=4, want_pass=True)
+        want = np.zeros((n, n), np.uint8)
+        edges = 0
+        for a, b in itertools.combinations(range(n), 2):
+            want[a, b] = oracle.screen(sk[a], sk[b], s)[1]
+            if want[a, b]:
+                pr = oracle.pair(sk[a], sk[b])
+                edges += pr.ani >= 0 and max(pr.af_a, pr.af_b) >= min_af
+        assert np.array_equal(r["pass"], want)
+        assert r["survivors"] == int(want.sum()) and r["edges"] == edges
