@@ -18,6 +18,7 @@
 
 namespace {
 
+constexpr uint8_t SKIP = 4;  // blanks inside a sequence line are dropped, not packed
 struct CodeTable {
     uint8_t t[256];
     CodeTable() {
@@ -25,6 +26,7 @@ struct CodeTable {
         t[(int)'C'] = t[(int)'c'] = 1;
         t[(int)'G'] = t[(int)'g'] = 2;
         t[(int)'T'] = t[(int)'t'] = 3;
+        t[(int)'\r'] = t[(int)' '] = t[(int)'\t'] = SKIP;
     }
 };
 const CodeTable kCode;
@@ -39,6 +41,56 @@ struct Packer {
             words.push_back(cur);
             cur = 0;
         }
+    }
+    // n bytes of one sequence line.  Returns the number of bases packed (blanks are dropped).  The common case -- no
+    // blank in the piece -- goes 32 bytes -> one word without a branch per base; a piece with blanks is redone
+    // base by base.
+    int64_t put_line(const uint8_t *s, int64_t n) {
+        const size_t w0 = words.size();
+        const uint64_t cur0 = cur;
+        const int64_t nb0 = n_bases;
+        uint8_t flags = 0;
+        int64_t k = 0;
+        const int sh = 2 * (int)(n_bases & 31);
+        for (; k + 32 <= n; k += 32) {
+            uint64_t w = 0;
+#pragma GCC unroll 32
+            for (int x = 0; x < 32; x++) {
+                const uint8_t c = kCode.t[s[k + x]];
+                flags |= c;
+                w |= (uint64_t)(c & 3) << (2 * x);
+            }
+            words.push_back(cur | (w << sh));
+            cur = sh ? w >> (64 - sh) : 0;
+        }
+        n_bases += k;
+        if (k < n) {  // the last r < 32 bytes: one partial word, merged the same way
+            const int r = (int)(n - k);
+            uint64_t w = 0;
+            for (int x = 0; x < r; x++) {
+                const uint8_t c = kCode.t[s[k + x]];
+                flags |= c;
+                w |= (uint64_t)(c & 3) << (2 * x);
+            }
+            cur |= w << sh;
+            if (sh + 2 * r >= 64) {
+                words.push_back(cur);
+                cur = sh ? w >> (64 - sh) : 0;
+            }
+            n_bases += r;
+        }
+        if (!(flags & SKIP)) return n;
+        words.resize(w0);  // rare: blanks inside the line
+        cur = cur0;
+        n_bases = nb0;
+        int64_t kept = 0;
+        for (k = 0; k < n; k++) {
+            const uint8_t c = kCode.t[s[k]];
+            if (c & SKIP) continue;
+            put(c);
+            kept++;
+        }
+        return kept;
     }
     void finish() {
         if (n_bases & 31) words.push_back(cur);
@@ -101,7 +153,7 @@ int skb_pack_fasta(const char *path, int32_t min_contig_len, skb_packed **out) {
     // Records are packed straight into the output; a record that turns out shorter than
     // min_contig_len is rolled back.
     Packer pk;
-    pk.words.reserve(1 << 16);
+    pk.words.reserve(1 << 18);
     std::vector<int64_t> kept, all_lens;
     std::string first_name, cur_name;
     bool have_first = false, in_header = false, in_record = false;
@@ -131,22 +183,19 @@ int skb_pack_fasta(const char *path, int32_t min_contig_len, skb_packed **out) {
             return SKB_EIO;
         }
         if (got == 0) break;
-        for (int i = 0; i < got; i++) {
-            char ch = buf[i];
-            if (in_header) {
-                if (ch == '\n') {
-                    in_header = false;
-                    at_line_start = true;
-                    while (!cur_name.empty() && cur_name.back() == '\r') cur_name.pop_back();
-                } else
-                    cur_name.push_back(ch);
-                continue;
-            }
-            if (ch == '\n') {
+        const char *p = buf.data(), *const end = p + got;
+        while (p < end) {
+            if (in_header) {  // the rest of the header line
+                const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+                cur_name.append(p, nl ? nl : end);
+                if (!nl) break;
+                in_header = false;
                 at_line_start = true;
+                while (!cur_name.empty() && cur_name.back() == '\r') cur_name.pop_back();
+                p = nl + 1;
                 continue;
             }
-            if (at_line_start && ch == '>') {
+            if (at_line_start && *p == '>') {
                 close_record();
                 in_record = true;
                 in_header = true;
@@ -155,13 +204,15 @@ int skb_pack_fasta(const char *path, int32_t min_contig_len, skb_packed **out) {
                 rec_start_bases = pk.n_bases;
                 rec_start_words = pk.words.size();
                 rec_start_cur = pk.cur;
+                p++;
                 continue;
             }
-            at_line_start = false;
-            if (ch == '\r' || ch == ' ' || ch == '\t') continue;
-            if (!in_record) continue;  // text before the first header
-            pk.put(kCode.t[(uint8_t)ch]);
-            rec_len++;
+            // (the rest of) a sequence line; a '>' that is not first on its line is an ordinary non-ACGT byte
+            const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+            const char *e = nl ? nl : end;
+            if (in_record && e > p) rec_len += pk.put_line((const uint8_t *)p, (int64_t)(e - p));  // else: text before the first header
+            at_line_start = nl != nullptr;
+            p = nl ? nl + 1 : end;
         }
     }
     gzclose(g);

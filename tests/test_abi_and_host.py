@@ -131,3 +131,60 @@ def test_synthetic_generator_is_deterministic():
     assert a == b and a != synth.one_clade(4, 2, 60_000, 11)
     g = list(synth.config_genomes("tiny"))
     assert len(g) == 12 and all(sum(map(len, c)) > 20_000 for _, _, c in g)
+
+
+def _reference_pack(txt, min_len):
+    """Plain-Python statement of the packer's rules (csrc/fasta_pack.cpp): '>' starts a record only as the first byte
+    of a line, blanks (CR, space, tab) inside sequence lines are dropped, C/G/T in either case are 1/2/3 and every other
+    byte is A, records shorter than min_len are left out, text before the first header is ignored."""
+    code = {ord("C"): 1, ord("c"): 1, ord("G"): 2, ord("g"): 2, ord("T"): 3, ord("t"): 3}
+    recs, cur = [], None
+    for line in txt.split(b"\n"):
+        if line[:1] == b">":
+            cur = []
+            recs.append(cur)
+        elif cur is not None:
+            cur.extend(code.get(c, 0) for c in line if c not in b"\r \t")
+    kept = [r for r in recs if len(r) >= min_len and len(r) > 0]
+    return [c for r in kept for c in r], [len(r) for r in kept], sum(len(r) for r in recs)
+
+
+def test_packer_line_shapes_against_plain_python(built_lib, tmp_path):
+    """Every line shape the fast paths see: lengths around the 32-base word, pieces that start at any offset inside a
+    word, blanks inside lines (slow path), CRLF, IUPAC codes, '>' inside a line, empty lines, no final newline, one
+    very long line, records that are rolled back -- plain and gzip, against a plain-Python restatement."""
+    from skder_b200 import engine
+
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKMSWryBDHV>", np.uint8)
+    parts = [b"text before any header\nACGT\n"]
+    for rec in range(40):
+        parts.append(b">rec%d some description\r\n" % rec if rec % 3 == 0 else b">rec%d\n" % rec)
+        for _ in range(int(rng.integers(0, 12))):
+            n = int(rng.choice([0, 1, 5, 31, 32, 33, 63, 64, 65, 80, 100, 257]))
+            line = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+            if line[:1] == b">":
+                line = b"A" + line[1:]
+            if rng.random() < 0.2 and n > 4:  # blanks inside the line
+                k = int(rng.integers(1, n - 1))
+                line = line[:k] + rng.choice([b" ", b"\t", b"\r", b"  \t"]) + line[k:]
+            parts.append(line + (b"\r\n" if rng.random() < 0.3 else b"\n"))
+    parts.append(b">long\n" + alphabet[rng.integers(0, 8, 70_001)].tobytes() + b"\n>last_no_newline\n" + b"ACGT" * 40)
+    txt = b"".join(parts)
+    plain = tmp_path / "shapes.fa"
+    plain.write_bytes(txt)
+    gz = tmp_path / "shapes.fa.gz"
+    with gzip.open(gz, "wb") as g:
+        g.write(txt)
+    for min_len in (1, 100, 500):
+        codes, lens, total_all = _reference_pack(txt, min_len)
+        for path in (plain, gz):
+            pk = engine.pack_fasta(str(path), min_len)
+            assert (pk.n_bases, pk.n_contigs, pk.total_bases_all) == (len(codes), len(lens), total_all)
+            assert pk.contig_lens().tolist() == lens
+            w = pk.words()
+            got = ((w[:, None] >> (2 * np.arange(32, dtype=np.uint64))[None, :]) & np.uint64(3)).reshape(-1)[: len(codes)]
+            assert np.array_equal(got.astype(np.int64), np.array(codes, np.int64))
+            assert not np.any(w[(len(codes) + 31) // 32:])  # padding words are zero
+            if len(codes) % 32:
+                assert int(w[len(codes) // 32]) >> (2 * (len(codes) % 32)) == 0  # and so are the unused bits
