@@ -73,6 +73,22 @@ def test_pack_and_oracle_ingest_agree_with_golden_n50(genomes7, built_lib):
         assert p.n50 == n50[_acc(f)], f  # reference util.n50_calc (src/skDER/util.py:686-724)
 
 
+def test_determine_n50_mirror_matches_golden(genomes7, built_lib, tmp_path):
+    """skder_b200.n50.determineN50 -- the stand-in for reference util.determineN50 (src/skDER/util.py:429-474)."""
+    from skder_b200 import n50 as n50_mod
+
+    want = {}
+    with open(os.path.join(GOLDEN, "skder_results", "Concatenated_N50.txt")) as f:
+        for line in f:
+            p, v = line.rstrip("\n").split("\t")
+            want[_acc(p)] = int(v)
+    listing = tmp_path / "All_Genomes_Listing.txt"
+    listing.write_text("".join(p + "\n" for p in genomes7))
+    got = n50_mod.determineN50(str(listing), str(tmp_path) + "/", None, threads=3)
+    assert list(got) == list(genomes7)
+    assert {_acc(p): v for p, v in got.items()} == {k: want[k] for k in (_acc(p) for p in genomes7)}
+
+
 def test_triangle_7_against_golden(oracle, sk7, genomes7):
     gold = _by_acc(load_edge_tsv(os.path.join(GOLDEN, "skder_results", "Skani_Triangle_Edge_Output.txt")))
     assert len(gold) == 21
