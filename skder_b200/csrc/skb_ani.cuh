@@ -140,7 +140,10 @@ __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, 
 
 // ---- K4a: anchors.  One warp per task; the only dependent reads are descriptor -> seed records ->
 // buckets, covered by the other resident warps.
-__global__ void __launch_bounds__(ANC_THREADS, 4)
+#ifndef SKB_ANC_MIN_CTAS
+#define SKB_ANC_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ANC_THREADS, SKB_ANC_MIN_CTAS)
 anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint32_t n_tasks,
               uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n, uint32_t *__restrict__ next_task) {
     __shared__ uint32_t stage_all[ANC_THREADS / 32][32 * STAGE];
