@@ -27,7 +27,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GREEDY_SCREEN = 89.5  # skDER default: -s (ANI cutoff 99.5 - 10)   reference bin/skder:199-204
+GREEDY_SCREEN = 89.5  # skDER default: -s (ANI cutoff 99.5 - 10)   reference bin/skder:199-204 (greedy AND dynamic mode;
+                      # dynamic lowers --min-af by 20 only together with -n, bin/skder:218-219)
 GREEDY_MIN_AF = 50.0  # skDER default AF cutoff                    reference bin/skder:325-329
 # bounded sample of the workload the CPU arm is timed on (same generator, same clade structure): 400 genomes,
 # 79,800 pairs, 1,800 survivors -- roughly 30 core-seconds of oracle work
@@ -155,7 +156,7 @@ def run_reference(args):
 
 def workload_name(w):
     nc, per, L = workload_shape(w)
-    return "%s: %d synthetic %.1f Mbp genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER greedy thresholds" % (
+    return "%s: %d synthetic %.1f Mbp genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER default thresholds: greedy and dynamic mode both run `skani triangle -s 89.5 --min-af 50 -E`" % (
         w, nc * per, L / 1e6, nc, per)
 
 
