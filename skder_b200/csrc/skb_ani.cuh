@@ -254,6 +254,12 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR) + x);
         }
         uint32_t outp[UNR];
+        // Upper bound on what any predecessor other than the nearest can offer: a candidate is F - gap <= F.  Mx is
+        // the largest F in the window behind the nearest predecessor (it may include one anchor just outside the
+        // window: an over-estimate only costs a missed short cut).
+        int Mx = F[UNR + 1];
+#pragma unroll
+        for (int u = UNR + 2; u < LB + UNR; u++) Mx = max(Mx, F[u]);
 #pragma unroll
         for (int x = 0; x < UNR; x++) {
             const uint64_t a = av[x];
@@ -264,9 +270,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             int best = prm.anchor_score;
             uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
             const int me = UNR - 1 - x;               // this anchor's slot
-#pragma unroll
-            for (int d = 0; d < LB; d++) {  // d = 0 is the nearest predecessor: ties keep it
-                const int sl = me + 1 + d;
+            auto relax = [&](int sl) {
                 const int dq1 = qi - Q[sl];  // dq - 1
                 const int dd = Di - D[sl];
                 const int dr1 = dd + dq1;    // d_ref - 1
@@ -276,7 +280,17 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                     best = cand;
                     brc = RC[sl];
                 }
+            };
+            relax(me + 1);  // d = 0, the nearest predecessor: ties keep it
+            // Colinear anchors (the usual case) chain onto the nearest predecessor with a score no other one can
+            // reach: when that holds for all 32 tasks of the warp the other 15 predecessors are not looked at.
+            // Same result as the full scan: a later d only replaces `best` with a strictly larger candidate.
+            const bool settled = i0 + x >= my_n || Mx <= best;
+            if (!__all_sync(0xffffffffu, settled)) {
+#pragma unroll
+                for (int d = 1; d < LB; d++) relax(me + 1 + d);
             }
+            Mx = max(Mx, F[me + 1]);  // the nearest predecessor is an "other" one for the next anchor
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;
             const bool live = i0 + x < my_n;

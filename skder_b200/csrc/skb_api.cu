@@ -115,6 +115,8 @@ struct skb_ctx {
     // built by skb_index
     bool indexed = false;
     int32_t n_indexed = 0;
+    int tab_x2 = 4;        // seed-table buckets per seed, times two: 4 / 2 / 1 = 0.5 / 1 / 2 records per 4-slot bucket
+    int tab_x2_forced = 0; // SKB_TAB_X2 (tests exercise the overflow chain with 1)
     DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
     DevBuf<uint32_t> d_tab_buckets;
     DevBuf<uint32_t> d_chunk_begin, d_chunk_start, d_chunk_len, d_chunk_off, d_ctg_pstart, d_ctg_len, d_ctg_off,
@@ -705,6 +707,10 @@ int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
         return SKB_ECUDA;
     }
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = std::getenv("SKB_TAB_X2")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) c->tab_x2_forced = v;
+    }
     *out = c;
     return SKB_OK;
 }
@@ -894,6 +900,21 @@ int skb_index(skb_ctx *ctx) {
         std::vector<uint64_t> &tab_off = c->h_tab_off;
         std::vector<uint32_t> &tab_buckets = c->h_tab_buckets, &ctg_pstart = c->h_ctg_pstart, &chunk_start = c->h_chunk_start,
                               &chunk_len = c->h_chunk_len;
+        // the sparsest seed tables the device holds comfortably: a lookup is one sector read unless its bucket
+        // overflowed, and at 0.5 records per bucket that is rare enough not to stall a warp (skb_probe.cuh)
+        c->tab_x2 = c->tab_x2_forced;
+        if (!c->tab_x2) {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const double budget = std::min(0.35 * (double)total_b,
+                                           (double)free_b + (double)c->d_tab.cap * 8.0 - 40.0 * (double)(1ull << 30));
+            c->tab_x2 = 1;
+            for (int x2 : {4, 2})
+                if (((double)n_seeds * x2 / 2 + (double)n) * BUCKET * 8.0 <= budget) {
+                    c->tab_x2 = x2;
+                    break;
+                }
+        }
         tab_off.assign(n + 1, 0);
         tab_buckets.assign(n, 0);
         ctg_pstart.assign(c->h_ctg_len.size(), 0);
@@ -903,7 +924,7 @@ int skb_index(skb_ctx *ctx) {
         for (int32_t g = 0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
             if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
-            tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns / 2 + 1);  // 4 slots per bucket: load factor 0.5
+            tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns * (uint64_t)c->tab_x2 / 2 + 1);
             tab_off[g + 1] = tab_off[g] + (uint64_t)tab_buckets[g] * BUCKET;
             uint32_t off = 0;
             for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
@@ -1017,7 +1038,7 @@ int skb_index_append(skb_ctx *ctx) {
         for (int32_t g = n0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
             if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
-            c->h_tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns / 2 + 1);
+            c->h_tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns * (uint64_t)c->tab_x2 / 2 + 1);
             c->h_tab_off[g + 1] = c->h_tab_off[g] + (uint64_t)c->h_tab_buckets[g] * BUCKET;
             uint32_t off = 0;
             for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {

@@ -17,7 +17,6 @@ constexpr uint64_t THR_MARKER = 0xFFFFFFFFFFFFFFFFull / C_MARKER;
 constexpr uint64_t MASK_MARKER = (~0ull) >> (64 - 2 * K_MARKER);
 constexpr uint64_t MASK_SEED = (~0ull) >> (64 - 2 * K_SEED);
 constexpr uint32_t CONTIG_PAD = 4096;  // virtual gap between contigs in genome coordinates
-constexpr int LOOKBACK = 32;           // chaining look-back in anchors == warp width
 
 // ---- packed seed record: kmer(30) << 34 | padded_pos(32) << 2 | rep << 1 | strand -------------
 __host__ __device__ inline uint32_t seed_kmer(uint64_t s) { return (uint32_t)(s >> 34); }
@@ -62,13 +61,9 @@ __host__ __device__ inline uint32_t rows_owned(uint32_t n, uint32_t part, uint32
     return 2 * (n / (2 * P)) + (rem > part ? 1u : 0u) + (rem > 2 * P - 1 - part ? 1u : 0u);
 }
 
-// Seed index layout: buckets of 4 slots (one 32-byte sector).  A k-mer's entries live in its home
-// bucket; a bucket that is full spills into the next one, so a lookup reads buckets until it meets
-// one with a free slot -- at load factor 0.5 that is 1.05 sectors on average, the same for every lane.
+// Seed index layout: buckets of 4 slots (one 32-byte sector), one home bucket per k-mer, overflow into the
+// following buckets behind a per-bucket flag (skb_probe.cuh).
 constexpr uint32_t BUCKET = 4;
-__host__ __device__ inline uint32_t tab_bucket(uint32_t kmer, uint32_t n_buckets) {
-    return (uint32_t)(((uint64_t)(uint32_t)(kmer * 0x9E3779B1u) * (uint64_t)n_buckets) >> 32);
-}
 
 // Device view of the sketch DB (all pointers device memory)
 struct DbView {
@@ -77,7 +72,7 @@ struct DbView {
     const uint64_t *g_seed_off;  // [n+1]
     const uint64_t *tab;         // open-addressing seed index, all genomes
     const uint64_t *g_tab_off;   // [n+1]
-    const uint32_t *g_tab_buckets; // [n] buckets per table (= seeds / 2 + 1), 4 slots each
+    const uint32_t *g_tab_buckets; // [n] buckets per table (seeds x 2, 1 or 1/2: skb_index), 4 slots each
     const uint32_t *chunk_begin; // genome g: n_chunks(g)+1 entries at g_chunk_off[g] + g (seed index relative to genome)
     const uint32_t *chunk_start; // [total chunks] padded coordinate of first base
     const uint32_t *chunk_len;   // [total chunks]

@@ -1,29 +1,34 @@
-// K2 -- per-reference seed index: two-choice bucketed hash table keyed by the seed k-mer, and the
-// batched anchor lookup the chunk kernel's P1 runs against it.
+// K2 -- per-reference seed index: bucketed hash table keyed by the seed k-mer, and the batched anchor
+// lookup the chunk kernel's P1 runs against it.
 //
 // Stand-in for skani's seed map (k-mer -> positions) used by the pairwise estimator behind
 // `skani triangle|dist|search` (reference call sites src/skDER/skder.py:16-18, :58-59, :119).
 //
-// Layout: buckets of 4 slots = one 32-byte sector.  A k-mer has two home buckets; an entry goes to the
-// emptier one, so at load factor 0.5 a full bucket is rare and both-full practically never happens
-// (then entries spill linearly after the first home).  A lookup therefore costs a FIXED two sector
-// reads issued together -- no dependent probe chain and no lane waiting for another lane's chain,
-// which is what bounded the linear-probing version (ncu: 37% of samples on the chain's scoreboard).
+// Layout: buckets of 4 slots = one 32-byte sector.  A k-mer has ONE home bucket; a record that finds it full
+// sets the bucket's overflow flag (bit 1 of slot 3 -- free in table copies, the repeat flag lives in the seed
+// array) and moves on to the next bucket, flagging every full bucket it passes.  A lookup reads the home bucket
+// and goes on only while the bucket it has just read is flagged.  Tables are built at load factor 0.5 / 1 / 2
+// entries per bucket (the sparsest the device memory budget allows, skb_index): at 0.5 a present k-mer's bucket
+// is flagged with probability 0.2%, so a lookup is ONE scattered sector read -- one L1 wavefront per lane
+// instead of the two of the two-choice layout this replaces (ncu, round 1: l1tex data-pipe wavefronts 83% of
+// peak, 2.3x the algorithmic bytes at L2) -- and the dependent second read is rare enough not to stall warps.
 #pragma once
 #include "skb_common.cuh"
 
 namespace skb {
 
-constexpr int PJ = 2;         // lookups in flight per lane in the batched probe
+#ifndef SKB_PJ
+#define SKB_PJ 4
+#endif
+constexpr int PJ = SKB_PJ;    // lookups in flight per lane in the batched probe
 constexpr int STAGE_CAP = 8;  // hits staged per seed (max_mult upper bound)
 
 __host__ __device__ inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 
-__host__ __device__ inline void tab_homes(uint32_t kmer, uint32_t nb, uint32_t &b1, uint32_t &b2) {
-    b1 = mulhi32(kmer * 0x9E3779B1u, nb);
-    b2 = mulhi32((kmer ^ (kmer >> 15)) * 0x85EBCA77u + 0x165667B1u, nb);
-    if (b2 == b1) b2 = (b1 + 1 == nb) ? 0 : b1 + 1;  // nb >= 2
-}
+__host__ __device__ inline uint32_t tab_home(uint32_t kmer, uint32_t nb) { return mulhi32(kmer * 0x9E3779B1u, nb); }
+__host__ __device__ inline uint32_t tab_next(uint32_t b, uint32_t nb) { return b + 1 == nb ? 0 : b + 1; }
+// slot 3 of a bucket: occupied and flagged "records continue in the next bucket"
+__host__ __device__ inline bool tab_flagged(uint64_t slot3) { return (slot3 & 2ull) && (~slot3 >> 34) != 0; }
 
 __device__ __forceinline__ int genome_of(const uint64_t *__restrict__ off, int n, uint64_t i) {
     int lo = 0, hi = n - 1;  // last g with off[g] <= i
@@ -57,83 +62,53 @@ __global__ void tab_insert_kernel(const uint64_t *__restrict__ seeds, uint64_t n
     const int g = genome_of_warp(g_seed_off, n_genomes, i < n_seeds ? i : n_seeds - 1);
     if (i >= n_seeds) return;
     const uint32_t nb = g_tab_buckets[g];
-    volatile unsigned long long *T = reinterpret_cast<volatile unsigned long long *>(tab + g_tab_off[g]);
+    unsigned long long *T = reinterpret_cast<unsigned long long *>(tab + g_tab_off[g]);
     const unsigned long long rec = seeds[i] & ~2ull;
-    uint32_t b1, b2;
-    tab_homes(seed_kmer(rec), nb, b1, b2);
+    uint32_t b = tab_home(seed_kmer(rec), nb);
     for (;;) {
-        // occupancy of both homes from two 256-bit reads (slots fill in order); .cg: other threads are inserting
-        unsigned long long a[BUCKET], c[BUCKET];
+        // occupancy from one 256-bit read (slots fill in order); .cg: other threads are inserting
+        unsigned long long a[BUCKET];
         asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(a[0]), "=l"(a[1]), "=l"(a[2]), "=l"(a[3]) : "l"(tab + g_tab_off[g] + (size_t)b1 * BUCKET) : "memory");
-        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3]) : "l"(tab + g_tab_off[g] + (size_t)b2 * BUCKET) : "memory");
-        int o1 = 0, o2 = 0;
+                     : "=l"(a[0]), "=l"(a[1]), "=l"(a[2]), "=l"(a[3]) : "l"(T + (size_t)b * BUCKET) : "memory");
+        int occ = 0;
 #pragma unroll
-        for (int k = 0; k < (int)BUCKET; k++) {
-            o1 += a[k] != TAB_EMPTY;
-            o2 += c[k] != TAB_EMPTY;
+        for (int k = 0; k < (int)BUCKET; k++) occ += a[k] != TAB_EMPTY;
+        if (occ < (int)BUCKET) {
+            if (atomicCAS(&T[(size_t)b * BUCKET + occ], (unsigned long long)TAB_EMPTY, rec) == TAB_EMPTY) return;
+            continue;  // somebody else took the slot: look again
         }
-        if (o1 == (int)BUCKET && o2 == (int)BUCKET) break;
-        const uint32_t tb = o2 < o1 ? b2 : b1;
-        const int slot = o2 < o1 ? o2 : o1;
-        if (atomicCAS(const_cast<unsigned long long *>(&T[(size_t)tb * BUCKET + slot]), (unsigned long long)TAB_EMPTY, rec) ==
-            TAB_EMPTY)
-            return;
-    }
-    // both homes full: spill linearly after the first home, skipping the second
-    uint32_t b = b1;
-    for (;;) {
-        b = (b + 1 == nb) ? 0 : b + 1;
-        if (b == b2) continue;
-        for (uint32_t j = 0; j < BUCKET; j++)
-            if (atomicCAS(const_cast<unsigned long long *>(&T[(size_t)b * BUCKET + j]), (unsigned long long)TAB_EMPTY, rec) ==
-                TAB_EMPTY)
-                return;
+        if (!(a[BUCKET - 1] & 2ull)) atomicOr(&T[(size_t)b * BUCKET + BUCKET - 1], 2ull);
+        b = tab_next(b, nb);
     }
 }
 
-struct Bucket2 {
-    ulonglong2 a0, a1, c0, c1;  // home 1 slots 0..3, home 2 slots 0..3
+struct Bucket {
+    ulonglong2 lo, hi;  // slots 0..3
 };
-__device__ __forceinline__ Bucket2 empty_buckets() {
-    Bucket2 B;
-    B.a0 = B.a1 = B.c0 = B.c1 = make_ulonglong2(TAB_EMPTY, TAB_EMPTY);
+__device__ __forceinline__ Bucket empty_bucket() {
+    Bucket B;
+    B.lo = B.hi = make_ulonglong2(TAB_EMPTY, TAB_EMPTY);
     return B;
 }
 // One bucket = one 32-byte sector = ONE 256-bit load (LDG.E.256, sm_100).  Lookups are scattered, so every load
-// instruction costs the L1 data pipe a wavefront per lane; with two 128-bit loads per bucket that pipe was the
-// anchor kernel's limit (ncu: l1tex data-pipe wavefronts 99.6% of peak).  Buckets are 32-byte aligned (table
-// offsets are multiples of BUCKET words, the allocation is 256-byte aligned).
-__device__ __forceinline__ void ld_bucket(const uint64_t *__restrict__ p, ulonglong2 &lo, ulonglong2 &hi) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(lo.x), "=l"(lo.y), "=l"(hi.x), "=l"(hi.y) : "l"(p));
-}
-__device__ __forceinline__ Bucket2 load_buckets(const uint64_t *__restrict__ T, uint32_t b1, uint32_t b2) {
-    Bucket2 B;
-    ld_bucket(T + (size_t)b1 * BUCKET, B.a0, B.a1);
-    ld_bucket(T + (size_t)b2 * BUCKET, B.c0, B.c1);
+// instruction costs the L1 data pipe a wavefront per lane.  Buckets are 32-byte aligned (table offsets are
+// multiples of BUCKET words, the allocation is 256-byte aligned).
+__device__ __forceinline__ Bucket load_bucket(const uint64_t *__restrict__ T, uint32_t b) {
+    Bucket B;
+    const uint64_t *p = T + (size_t)b * BUCKET;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(B.lo.x), "=l"(B.lo.y), "=l"(B.hi.x), "=l"(B.hi.y) : "l"(p));
     return B;
 }
-__device__ __forceinline__ bool both_full(const Bucket2 &B) { return B.a1.y != TAB_EMPTY && B.c1.y != TAB_EMPTY; }
 
 // entries holding `kmer` (an empty slot's k-mer field, all ones, is never a canonical k-mer)
 __device__ __forceinline__ int tab_count(const uint64_t *__restrict__ T, uint32_t nb, uint32_t kmer, int cap) {
-    uint32_t b1, b2;
-    tab_homes(kmer, nb, b1, b2);
-    const Bucket2 B = load_buckets(T, b1, b2);
-    int c = (seed_kmer(B.a0.x) == kmer) + (seed_kmer(B.a0.y) == kmer) + (seed_kmer(B.a1.x) == kmer) +
-            (seed_kmer(B.a1.y) == kmer) + (seed_kmer(B.c0.x) == kmer) + (seed_kmer(B.c0.y) == kmer) +
-            (seed_kmer(B.c1.x) == kmer) + (seed_kmer(B.c1.y) == kmer);
-    if (both_full(B)) {
-        uint32_t b = b1;
-        for (;;) {
-            b = (b + 1 == nb) ? 0 : b + 1;
-            if (b == b2) continue;
-            ulonglong2 x0, x1;
-            ld_bucket(T + (size_t)b * BUCKET, x0, x1);
-            c += (seed_kmer(x0.x) == kmer) + (seed_kmer(x0.y) == kmer) + (seed_kmer(x1.x) == kmer) + (seed_kmer(x1.y) == kmer);
-            if (x1.y == TAB_EMPTY || c >= cap) break;
-        }
+    uint32_t b = tab_home(kmer, nb);
+    int c = 0;
+    for (;;) {
+        const Bucket B = load_bucket(T, b);
+        c += (seed_kmer(B.lo.x) == kmer) + (seed_kmer(B.lo.y) == kmer) + (seed_kmer(B.hi.x) == kmer) + (seed_kmer(B.hi.y) == kmer);
+        if (!tab_flagged(B.hi.y) || c >= cap) break;
+        b = tab_next(b, nb);
     }
     return c;
 }
@@ -156,51 +131,47 @@ __device__ __forceinline__ uint32_t enc_hit(uint64_t e, uint64_t sd) {
     return (seed_pos(e) << 1) | (uint32_t)(seed_strand(e) != seed_strand(sd));
 }
 
-// One lookup of the batch: lane's seed `sd` with its two home buckets B already loaded.  Appends the
+// One lookup of the batch: lane's seed `sd` with its home bucket B already loaded.  Appends the
 // seed's anchors (if it has 1..mult hits) after `base`; returns base + anchors of all 32 lanes.
-__device__ __forceinline__ int probe_one(uint64_t sd, const Bucket2 &B, const uint64_t *__restrict__ T, uint32_t nb,
+__device__ __forceinline__ int probe_one(uint64_t sd, const Bucket &B, const uint64_t *__restrict__ T, uint32_t nb,
                                          int mult, int max_mult, int max_anchors, uint32_t *stage, uint64_t *anc,
                                          int base, int s, uint32_t cstart, int lane) {
     const uint32_t km = seed_kmer(sd);
-    const uint64_t e8[8] = {B.a0.x, B.a0.y, B.a1.x, B.a1.y, B.c0.x, B.c0.y, B.c1.x, B.c1.y};
+    const uint64_t e4[4] = {B.lo.x, B.lo.y, B.hi.x, B.hi.y};
     // the k-mer is the top 30 bits of a record: compare on the high word only.  Flagged / out-of-range
-    // lanes hold all-empty buckets, whose k-mer field (all ones) is never a canonical k-mer.
+    // lanes hold an all-empty bucket, whose k-mer field (all ones) is never a canonical k-mer.
     const uint32_t kmhi = km << 2;
     int c = 0;
     uint64_t e1 = 0;  // the hit when there is exactly one
 #pragma unroll
-    for (int x = 0; x < 8; x++) {
-        const bool hit = (((uint32_t)(e8[x] >> 32)) ^ kmhi) < 4u;
+    for (int x = 0; x < 4; x++) {
+        const bool hit = (((uint32_t)(e4[x] >> 32)) ^ kmhi) < 4u;
         c += hit;
-        if (hit) e1 = e8[x];
+        if (hit) e1 = e4[x];
     }
-    const bool spilled = both_full(B);  // practically never: both homes full -> entries may have spilled
+    const bool spilled = tab_flagged(B.hi.y);  // rare: the k-mer's records may continue in the next bucket(s)
     const bool slow = spilled || c > 1;
     if (slow) {  // rare: repeats or spill -> stage all hits, sorted by ref position
         int cc = 0;
 #pragma unroll
-        for (int x = 0; x < 8; x++)
-            if ((((uint32_t)(e8[x] >> 32)) ^ kmhi) < 4u) {
-                if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e8[x], sd);
+        for (int x = 0; x < 4; x++)
+            if ((((uint32_t)(e4[x] >> 32)) ^ kmhi) < 4u) {
+                if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e4[x], sd);
                 cc++;
             }
         if (spilled) {
-            uint32_t b1, b2;
-            tab_homes(km, nb, b1, b2);
-            uint32_t b = b1;
+            uint32_t b = tab_home(km, nb);
             for (;;) {
-                b = (b + 1 == nb) ? 0 : b + 1;
-                if (b == b2) continue;
-                ulonglong2 x0, x1;
-                ld_bucket(T + (size_t)b * BUCKET, x0, x1);
-                const uint64_t e4[4] = {x0.x, x0.y, x1.x, x1.y};
+                b = tab_next(b, nb);
+                const Bucket X = load_bucket(T, b);
+                const uint64_t x4[4] = {X.lo.x, X.lo.y, X.hi.x, X.hi.y};
 #pragma unroll
                 for (int x = 0; x < 4; x++)
-                    if (seed_kmer(e4[x]) == km) {
-                        if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(e4[x], sd);
+                    if (seed_kmer(x4[x]) == km) {
+                        if (cc < STAGE_CAP) stage[lane * STAGE_CAP + cc] = enc_hit(x4[x], sd);
                         cc++;
                     }
-                if (x1.y == TAB_EMPTY || cc > max_mult) break;
+                if (!tab_flagged(X.hi.y) || cc > max_mult) break;
             }
         }
         c = cc;
@@ -268,16 +239,11 @@ __device__ __forceinline__ int emit_anchors(const uint64_t *__restrict__ qs, int
     int base = 0;
     for (int s0 = 0; s0 < nseeds; s0 += 32 * PJ) {
         uint64_t sd[PJ];
-        Bucket2 B[PJ];
+        Bucket B[PJ];
 #pragma unroll
         for (int j = 0; j < PJ; j++) {
             sd[j] = sdn[j];
-            if (!seed_rep(sd[j])) {
-                uint32_t b1, b2;
-                tab_homes(seed_kmer(sd[j]), nb, b1, b2);
-                B[j] = load_buckets(T, b1, b2);
-            } else
-                B[j] = empty_buckets();
+            B[j] = seed_rep(sd[j]) ? empty_bucket() : load_bucket(T, tab_home(seed_kmer(sd[j]), nb));
         }
         if (s0 + 32 * PJ < nseeds) {
 #pragma unroll
