@@ -42,10 +42,9 @@ typedef struct {
     int32_t min_anchors;    /* 3 */
     int32_t min_score;      /* 45 */
     int32_t max_mult;       /* 8 */
-    int32_t max_chunk_chains; /* 4 */
+    int32_t max_chunk_chains; /* 8 */
     int32_t ovl_num, ovl_den; /* 1/2 */
-    int32_t span_ext;       /* 150 */
-    int32_t min_chunk_seeds;/* 1 */
+    int32_t span_ext;       /* 170 */
     double debias_a, debias_g; /* learned-debias substitute: 100-ANI = a*(100-raw)^g */
 } skb_params;
 void skb_default_params(skb_params *p);
@@ -118,7 +117,7 @@ typedef struct {
     uint32_t a, b;
     double ani, ani_raw, af_a, af_b; /* fractions in [0,1]; ani < 0 if no estimate */
     int64_t n_anchors, n_seeds, span_q, span_r;
-    int32_t n_chains, n_chunks_used, swapped, overflow;
+    int32_t n_chains, swapped;
 } skb_pair_detail;
 
 typedef struct {

@@ -42,12 +42,10 @@ class Params(C.Structure):
         ("max_mult", C.c_int32),
         ("max_chunk_anchors", C.c_int32),
         ("max_chunk_chains", C.c_int32),
-        ("max_pair_chains", C.c_int32),
         ("ovl_num", C.c_int32),
         ("ovl_den", C.c_int32),
         ("span_ext", C.c_int32),
         ("role_rule", C.c_int32),
-        ("min_chunk_seeds", C.c_int32),
     ]
 
 
@@ -71,11 +69,8 @@ class PairResult(C.Structure):
         ("ani_raw", C.c_double),
         ("af_a", C.c_double),
         ("af_b", C.c_double),
-        ("std_chunk", C.c_double),
-        ("n_chunks_used", C.c_int32),
         ("n_chains", C.c_int32),
         ("swapped", C.c_int32),
-        ("overflow", C.c_int32),
         ("n_anchors_total", C.c_int64),
         ("n_seeds_total", C.c_int64),
         ("span_q", C.c_int64),

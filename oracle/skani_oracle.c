@@ -51,13 +51,11 @@ void ora_default_params(ora_params_t *p) {
     p->min_score = 45;
     p->max_mult = 8;
     p->max_chunk_anchors = 256;
-    p->max_chunk_chains = 4;
-    p->max_pair_chains = 1024;
+    p->max_chunk_chains = 8;
     p->ovl_num = 1;
     p->ovl_den = 2;
-    p->span_ext = 150;
+    p->span_ext = 170;
     p->role_rule = 0;
-    p->min_chunk_seeds = 1;
 }
 
 /* Invertible 64-bit mix used by skani/minimap2 for k-mer hashing (Appendix A of SURVEY.md).
@@ -388,8 +386,8 @@ static int64_t seeds_in_span(const ora_sketch_t *q, int32_t ch, uint32_t q0, uin
  * by a power law fitted ONCE, openly, to the 561 golden pairs of
  * test_case/skder_gtdb_results/Skani_Triangle_Edge_Output.txt (fit script: oracle/fit_debias.py):
  *   100-ANI_reported = DEBIAS_A * (100-ANI_raw)^DEBIAS_G      [percent units] */
-#define DEBIAS_A 1.49745019
-#define DEBIAS_G 0.8781001
+#define DEBIAS_A 1.438713
+#define DEBIAS_G 0.905292
 double ora_debias(double ani_raw) {
     double x = 100.0 * (1.0 - ani_raw);
     if (x <= 0.0) return 1.0;
@@ -421,8 +419,7 @@ int ora_pair(const ora_sketch_t *a, const ora_sketch_t *b, const ora_params_t *p
     size_t ccap = 1024, nc = 0;
     ora_chain_t *cands = (ora_chain_t *)malloc(sizeof(ora_chain_t) * ccap);
 
-    int chunk_cap = p->max_chunk_chains;
-retry:
+    const int chunk_cap = p->max_chunk_chains;
     nc = 0;
     for (int32_t ch = 0; ch < q->n_chunks; ch++) {
         /* anchors; if the chunk overflows, halve the multiplicity cap until it fits */
@@ -497,15 +494,6 @@ retry:
             nc = first + (size_t)chunk_cap;
         }
     }
-    /* a pair keeps at most max_pair_chains candidates: halve the per-chunk cap until it fits */
-    if (nc > (size_t)p->max_pair_chains) {
-        if (chunk_cap > 1) {
-            chunk_cap >>= 1;
-            goto retry;
-        }
-        nc = 0; /* > max_pair_chains chunks with a chain: not representable (the GPU path errors out) */
-        out->overflow = 1;
-    }
     /* pair-level selection: best score first; reject a chain overlapping an accepted one by more
      * than ovl_num/ovl_den of its own length on the reference or on the query */
     qsort(cands, nc, sizeof(ora_chain_t), cmp_cand);
@@ -523,65 +511,50 @@ retry:
         }
         if (ok) cands[na++] = *c;
     }
-    /* per-chunk ANI = (anchors / query seeds in chained span)^(1/k); genome ANI = mean over chunks
-     * weighted by seeds; AF = chained span / genome length */
-    int32_t nchunks = q->n_chunks;
-    int64_t *A = (int64_t *)calloc((size_t)(nchunks ? nchunks : 1), 8);
-    int64_t *S = (int64_t *)calloc((size_t)(nchunks ? nchunks : 1), 8);
+    /* ANI: anchors over query seeds inside the accepted chains, pooled over the pair.  The two END anchors of a
+     * chain are anchors by construction (they define the span the seeds are counted in), so they are left out of
+     * both counts -- otherwise short chains (fragmented assemblies) bias the ratio upward.  ANI_raw = ratio^(1/k).
+     * AF: covered bases = the k-mer span first..last anchor, extended by span_ext on both sides (the homology
+     * boundary lies about one anchor spacing beyond the outermost anchors).  An extension is cut where EITHER
+     * genome runs out -- the query chunk or the reference contig, at the matching end (for a reverse chain the
+     * query's left end faces the reference's high end) -- and applies to both spans alike. */
     int64_t span_q = 0, span_r = 0, At = 0, St = 0;
     for (size_t i = 0; i < na; i++) {
-        A[cands[i].chunk] += cands[i].n_anchors;
-        S[cands[i].chunk] += cands[i].n_seeds;
-        /* covered bases: the k-mer span first..last anchor, extended by span_ext on both sides
-         * (the homology boundary lies about one anchor spacing beyond the outermost anchors),
-         * clipped to the query chunk and to the reference contig */
-        {
-            int64_t k1 = p->k - 1, e = p->span_ext;
-            int64_t cs = q->chunk_start[cands[i].chunk], ce = cs + q->chunk_len[cands[i].chunk] - 1;
-            int64_t a0 = (int64_t)cands[i].q0 - k1 - e, a1 = (int64_t)cands[i].q1 + e;
-            if (a0 < cs) a0 = cs;
-            if (a1 > ce) a1 = ce;
-            span_q += a1 - a0 + 1;
-            int32_t lo = 0, hi = r->n_contigs - 1; /* contig holding r0 */
-            while (lo < hi) {
-                int32_t mid = (lo + hi + 1) >> 1;
-                if (r->contig_off[mid] <= cands[i].r0)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            int64_t rs = r->contig_off[lo], re = rs + r->contig_len[lo] - 1;
-            int64_t b0 = (int64_t)cands[i].r0 - k1 - e, b1 = (int64_t)cands[i].r1 + e;
-            if (b0 < rs) b0 = rs;
-            if (b1 > re) b1 = re;
-            span_r += b1 - b0 + 1;
+        const ora_chain_t *c = &cands[i];
+        const int64_t k1 = p->k - 1, e = p->span_ext;
+        const int64_t cs = q->chunk_start[c->chunk], ce = cs + q->chunk_len[c->chunk] - 1;
+        int32_t lo = 0, hi = r->n_contigs - 1; /* contig holding r0 */
+        while (lo < hi) {
+            int32_t mid = (lo + hi + 1) >> 1;
+            if (r->contig_off[mid] <= c->r0)
+                lo = mid;
+            else
+                hi = mid - 1;
         }
-        At += cands[i].n_anchors;
-        St += cands[i].n_seeds;
-    }
-    double sw = 0, sx = 0, sxx = 0;
-    int used = 0;
-    for (int32_t ch = 0; ch < nchunks; ch++) {
-        if (S[ch] < p->min_chunk_seeds || A[ch] == 0) continue;
-        double ratio = (double)A[ch] / (double)S[ch];
-        if (ratio > 1.0) ratio = 1.0;
-        double x = pow(ratio, 1.0 / (double)p->k);
-        double w = (double)S[ch];
-        sw += w;
-        sx += w * x;
-        sxx += w * x * x;
-        used++;
+        const int64_t rs = r->contig_off[lo], re = rs + r->contig_len[lo] - 1;
+        const int64_t a0 = (int64_t)c->q0 - k1, a1 = c->q1, b0 = (int64_t)c->r0 - k1, b1 = c->r1;
+        const int64_t room_ql = a0 - cs, room_qr = ce - a1, room_rlo = b0 - rs, room_rhi = re - b1;
+        int64_t el = c->rev ? room_rhi : room_rlo, er = c->rev ? room_rlo : room_rhi;
+        if (room_ql < el) el = room_ql;
+        if (room_qr < er) er = room_qr;
+        if (e < el) el = e;
+        if (e < er) er = e;
+        if (el < 0) el = 0;
+        if (er < 0) er = 0;
+        span_q += a1 - a0 + 1 + el + er;
+        span_r += b1 - b0 + 1 + el + er;
+        At += c->n_anchors;
+        St += c->n_seeds;
     }
     out->n_chains = (int32_t)na;
-    out->n_chunks_used = used;
     out->n_anchors_total = At;
     out->n_seeds_total = St;
     out->span_q = span_q;
     out->span_r = span_r;
-    if (used > 0 && sw > 0) {
-        double mean = sx / sw;
-        double var = sxx / sw - mean * mean;
-        out->std_chunk = var > 0 ? sqrt(var) : 0.0;
+    if (St - 2 * (int64_t)na > 0 && At - 2 * (int64_t)na > 0) {
+        double ratio = (double)(At - 2 * (int64_t)na) / (double)(St - 2 * (int64_t)na);
+        if (ratio > 1.0) ratio = 1.0;
+        const double mean = pow(ratio, 1.0 / (double)p->k);
         out->ani_raw = mean;
         double afq = (double)span_q / (double)q->total_len, afr = (double)span_r / (double)r->total_len;
         if (afq > 1.0) afq = 1.0;
@@ -596,8 +569,6 @@ retry:
         memcpy(chains_out, cands, sizeof(ora_chain_t) * (size_t)m);
         if (n_chains_out) *n_chains_out = m;
     }
-    free(A);
-    free(S);
     free(an);
     free(f);
     free(root);

@@ -10,7 +10,7 @@
  * bioconda_recipe/meta.yaml:28) whose source is absent from /root/reference. This file therefore
  * restates the PUBLISHED method (Shaw & Yu, Nat. Methods 2023, cited at reference README.md:436):
  * FracMinHash seeds (k=15, c=125) and markers (k=21, c=1000), marker-containment prescreen,
- * seed anchoring, banded chaining per 20 kb query chunk, per-chunk ANI = (anchors/seeds)^(1/k),
+ * seed anchoring, banded chaining per 20 kb query chunk, ANI = (anchors/seeds inside the chains)^(1/k),
  * AF = chained span / genome length. Details skani does not publish (and its learned ANI
  * debiasing model, whose weights are unavailable) are stated in DESIGN.md section 3.
  *
@@ -46,13 +46,11 @@ typedef struct {
     int32_t min_score;      /* score a chain needs (45) */
     int32_t max_mult;       /* seeds whose k-mer occurs more often in either genome are skipped */
     int32_t max_chunk_anchors; /* anchors kept per chunk (256) */
-    int32_t max_chunk_chains;  /* chain candidates kept per chunk (4) */
-    int32_t max_pair_chains;   /* chain candidates kept per pair (1024) */
+    int32_t max_chunk_chains;  /* chain candidates kept per chunk (8) */
     int32_t ovl_num;        /* chain rejected if overlap*ovl_den > ovl_num*own_length ... */
     int32_t ovl_den;        /* ... with an accepted chain on the reference or the query */
-    int32_t span_ext;       /* bases each accepted chain is extended by on both sides, clipped (150; fitted) */
+    int32_t span_ext;       /* bases each accepted chain is extended by on both sides, clipped (170; scanned, see fit_debias.py) */
     int32_t role_rule;      /* 0: query = fewer seeds (ties: lower index) ; 1: query = more seeds */
-    int32_t min_chunk_seeds;/* chunk contributes to ANI only if its chained span holds >= this many query seeds */
 } ora_params_t;
 
 /* one accepted chain, for diagnostics and calibration */
@@ -71,11 +69,8 @@ typedef struct {
     double ani_raw;     /* before debias */
     double af_a;        /* aligned fraction of genome a in [0,1] */
     double af_b;
-    double std_chunk;   /* sd of per-chunk ANI */
-    int32_t n_chunks_used;
     int32_t n_chains;
     int32_t swapped;    /* 1 if b was the query */
-    int32_t overflow;   /* 1 if the pair exceeded max_pair_chains */
     int64_t n_anchors_total;
     int64_t n_seeds_total;
     int64_t span_q, span_r;

@@ -25,7 +25,6 @@ class Params(C.Structure):
         ("ovl_num", C.c_int32),
         ("ovl_den", C.c_int32),
         ("span_ext", C.c_int32),
-        ("min_chunk_seeds", C.c_int32),
         ("debias_a", C.c_double),
         ("debias_g", C.c_double),
     ]
@@ -61,9 +60,7 @@ class PairDetail(C.Structure):
         ("span_q", C.c_int64),
         ("span_r", C.c_int64),
         ("n_chains", C.c_int32),
-        ("n_chunks_used", C.c_int32),
         ("swapped", C.c_int32),
-        ("overflow", C.c_int32),
     ]
 
 

@@ -18,9 +18,10 @@
 //   K4c ends_kernel (warp per task): best end of every DP tree with >= min_anchors / min_score; the
 //      chunk's top `max_chunk_chains` by (score, q0, r0) go to the task's fixed candidate slots.
 // finalize_kernel: one CTA per pair gathers the candidates, orders them by (score desc, chunk,
-//   ordinal), resolves the greedy non-overlap selection in parallel rounds, accumulates per-chunk
-//   anchors/seeds and clipped spans, and reduces ANI = sum(S_c (A_c/S_c)^(1/15)) / sum(S_c),
-//   AF = span / genome length.
+//   ordinal), resolves the greedy non-overlap selection in parallel rounds, sums anchors, seeds and the
+//   symmetrically clipped spans of the accepted chains, and reduces ANI = ((A - 2n) / (S - 2n))^(1/15) (n chains,
+//   end anchors left out), AF = span / genome length.  Pairs with more than MAXP candidates run the same code on
+//   global scratch (finalize_kernel<true>).
 #pragma once
 #include "skb_common.cuh"
 #include "skb_index.cuh"
@@ -33,16 +34,15 @@ constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA 
 constexpr int DP_THREADS = 128;               // K4b: one task per thread
 constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA pass
 constexpr int MAXA = 256;                     // anchors per chunk
-constexpr int MAXP = 1024;                    // chain candidates per pair
+constexpr int MAXP = 4096;                    // chain candidates per pair the shared-memory finalize kernel takes
 constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
 constexpr int ENDS_K = 8;                     // qualifying DP trees per chunk tracked inside chain_kernel
-constexpr int SLOTS = 4;                      // candidate slots per task (max_chunk_chains upper bound)
+constexpr int SLOTS = 8;                      // candidate slots per task (max_chunk_chains upper bound)
 constexpr int FIN_THREADS = 256;
-constexpr uint32_t FIN_MAX_CHUNKS = 4096;     // chunks of a query genome the finalize kernel accumulates in smem
 
 struct AniParams {
     int32_t band_bp, max_gap, anchor_score, min_anchors, min_score, max_mult, max_chunk_chains;
-    int32_t ovl_num, ovl_den, span_ext, min_chunk_seeds;
+    int32_t ovl_num, ovl_den, span_ext;
     double debias_a, debias_g;
 };
 
@@ -530,68 +530,86 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* [FIN_TH
 }
 
 struct FinCtl {
-    int n_cand, unresolved, n_acc, pad;
-    unsigned long long span_q, span_r, a_tot, s_tot;
+    int n_cand, unresolved;
     double red[FIN_THREADS / 32];
 };
 
-// dynamic smem: Cand[MAXP] | uint64 keys[MAXP] | uint8 state[MAXP] | uint32 accA[nch], accS[nch]
-constexpr size_t FIN_SMEM_FIXED = sizeof(Cand) * MAXP + 8 * MAXP + MAXP;
+// Candidates a pair brings to the selection (sum of its chunks' candidate counts).  Pairs with at most MAXP go
+// through the shared-memory finalize kernel, whose launch is sized for the largest of them in the batch
+// (max_small); the others -- a query of thousands of contigs against a close relative -- are listed for the
+// global-memory instance (finalize_kernel<true>): no pair is ever dropped or capped.
+__global__ void pair_ncand_kernel(const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off, uint32_t base,
+                                  int64_t n_pairs, const uint8_t *__restrict__ task_ncand, uint32_t *__restrict__ pair_nc,
+                                  uint32_t *ctl /* [0] max over small pairs, [1] number of big pairs */,
+                                  uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_nc) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t t0 = task_off[p] - base, nch = info[p].nch;
+    uint32_t nc = 0;
+    for (uint32_t ch = 0; ch < nch; ch++) nc += task_ncand[t0 + ch];
+    pair_nc[p] = nc;
+    if (nc <= (uint32_t)MAXP)
+        atomicMax(&ctl[0], nc);
+    else {
+        const uint32_t k = atomicAdd(&ctl[1], 1u);
+        big_list[k] = (uint32_t)p;
+        big_nc[k] = nc;
+    }
+}
 
+constexpr size_t FIN_BYTES_PER_CAND = sizeof(Cand) + 8 + 1;  // candidate + sort key + state
+
+// sort key of a candidate: score desc, chunk, ordinal within the chunk (= (q0, r0) order), then its slot
+//   (8191 - score)(13) << 51 | chunk(23) << 28 | ordinal(4) << 24 | slot(24)
+constexpr uint32_t FIN_IDX_MASK = 0xffffffu;
+constexpr uint32_t MAX_CHUNKS_PER_GENOME = 1u << 23;
+
+// BIG = false: one CTA per pair of the batch, candidates / keys / states in dynamic shared memory sized for `cap`
+//   candidates (a power of two >= the batch's largest small pair): Cand[cap] | u64 key[cap] | u8 state[cap].
+// BIG = true: one CTA per listed pair, the same three arrays in global scratch at big_off[blockIdx.x] (bytes),
+//   capacity big_cap[blockIdx.x].
+template <bool BIG>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
                 uint32_t base, int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
-                const uint32_t *__restrict__ perm, PairOut *__restrict__ out) {
+                const uint32_t *__restrict__ pair_nc, const uint32_t *__restrict__ perm, PairOut *__restrict__ out,
+                uint32_t cap, const uint32_t *__restrict__ big_list, const unsigned long long *__restrict__ big_off,
+                const uint32_t *__restrict__ big_cap, unsigned char *__restrict__ big_scratch) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FinCtl ctl;
-    Cand *cands = reinterpret_cast<Cand *>(smem);
-    uint64_t *skey = reinterpret_cast<uint64_t *>(smem + sizeof(Cand) * MAXP);
-    uint8_t *state = smem + sizeof(Cand) * MAXP + 8 * MAXP;
-    uint32_t *accA = reinterpret_cast<uint32_t *>(smem + FIN_SMEM_FIXED);
     const int tid = threadIdx.x;
-    const int64_t p = blockIdx.x;
+    int64_t p = blockIdx.x;
+    unsigned char *buf = smem;
+    if (BIG) {
+        p = big_list[blockIdx.x];
+        cap = big_cap[blockIdx.x];
+        buf = big_scratch + big_off[blockIdx.x];
+    }
     if (p >= n_pairs) return;
+    const int nc = (int)pair_nc[p];
+    if (!BIG && nc > MAXP) return;  // finalize_kernel<true> does this pair
+    Cand *cands = reinterpret_cast<Cand *>(buf);
+    uint64_t *skey = reinterpret_cast<uint64_t *>(buf + sizeof(Cand) * (size_t)cap);
+    uint8_t *state = buf + (sizeof(Cand) + 8) * (size_t)cap;
     const PairInfo pi = info[p];
     const uint32_t nch = pi.nch, t0 = task_off[p] - base;
     const uint32_t choff = db.g_chunk_off[pi.q];
-    uint32_t *accS = accA + nch;
-    int overflow = nch > FIN_MAX_CHUNKS;
-    // ---- how many candidates per chunk may stay so that the pair fits MAXP (oracle: halve the cap)
-    int cap = overflow ? 0 : prm.max_chunk_chains;
-    while (cap > 0) {
-        int local = 0;
-        for (uint32_t ch = tid; ch < nch; ch += FIN_THREADS) {
-            const int c = task_ncand[t0 + ch];
-            local += c < cap ? c : cap;
-        }
-        const int total = (int)block_sum((double)local, ctl.red, tid);
-        if (total <= MAXP) break;
-        cap >>= 1;
-        if (cap == 0) overflow = 1;
-    }
-    if (tid == 0) {
-        ctl.n_cand = 0;
-        ctl.span_q = ctl.span_r = ctl.a_tot = ctl.s_tot = 0;
-        ctl.n_acc = 0;
-    }
-    for (uint32_t i = tid; i < 2 * nch && !overflow; i += FIN_THREADS) accA[i] = 0;
+    if (tid == 0) ctl.n_cand = 0;
     __syncthreads();
-    for (uint32_t ch = tid; ch < nch && cap > 0; ch += FIN_THREADS) {
-        int c = task_ncand[t0 + ch];
-        c = c < cap ? c : cap;
+    for (uint32_t ch = tid; ch < nch; ch += FIN_THREADS) {
+        const int c = task_ncand[t0 + ch];
         if (c) {
             const int at = atomicAdd(&ctl.n_cand, c);
             for (int x = 0; x < c; x++) cands[at + x] = gcands[(size_t)(t0 + ch) * SLOTS + x];
         }
     }
     __syncthreads();
-    const int nc = ctl.n_cand;
     int m = 1;
     while (m < nc) m <<= 1;
     for (int i = tid; i < m; i += FIN_THREADS) {
         if (i < nc) {
             const Cand &c = cands[i];
-            skey[i] = ((uint64_t)(16383 - c.score) << 48) | ((uint64_t)c.chunk << 16) | ((uint64_t)c.ordinal << 12) |
+            skey[i] = ((uint64_t)(8191u - c.score) << 51) | ((uint64_t)c.chunk << 28) | ((uint64_t)c.ordinal << 24) |
                       (uint64_t)i;
         } else
             skey[i] = ~0ull;
@@ -626,11 +644,11 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
                 const int t = side ? nc - 1 - w0 : w0;
                 if (side && t == w0) break;
                 if (state[t]) continue;
-                const uint4 cr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[t] & 0xfff)]);  // q0 q1 r0 r1
+                const uint4 cr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[t] & FIN_IDX_MASK)]);  // q0 q1 r0 r1
                 const long long lq = (long long)cr.y - cr.x + 1, lr = (long long)cr.w - cr.z + 1;
                 int verdict = 1;
                 for (int u = 0; u < t; u++) {
-                    const uint4 dr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[u] & 0xfff)]);
+                    const uint4 dr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[u] & FIN_IDX_MASK)]);
                     // intervals that do not even touch (the usual case) cannot block: two compares each
                     const bool tq = dr.x <= cr.y && cr.x <= dr.y, tr = dr.z <= cr.w && cr.z <= dr.w;
                     if (!tq && !tr) continue;
@@ -656,7 +674,7 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         __syncthreads();
         if (!ctl.unresolved) break;
     }
-    // accumulate accepted chains
+    // accumulate accepted chains: anchors / seeds (pooled), spans with the symmetric clipped extension
     const uint32_t rcoff = db.g_ctg_off[pi.r];
     const int nrc = (int)(db.g_ctg_off[pi.r + 1] - rcoff);
     int n_acc_local = 0;
@@ -664,14 +682,9 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
     for (int t = tid; t < nc; t += FIN_THREADS) {
         if (state[t] != 1) continue;
         n_acc_local++;
-        const Cand &c = cands[(int)(skey[t] & 0xfff)];
-        atomicAdd(&accA[c.chunk], (uint32_t)c.n_anchors);
-        atomicAdd(&accS[c.chunk], (uint32_t)c.n_seeds);
+        const Cand &c = cands[(int)(skey[t] & FIN_IDX_MASK)];
         const long long e = prm.span_ext, k1 = K_SEED - 1;
         const long long cs = db.chunk_start[choff + c.chunk], ce = cs + db.chunk_len[choff + c.chunk] - 1;
-        long long a0 = (long long)c.q0 - k1 - e, a1 = (long long)c.q1 + e;
-        a0 = a0 < cs ? cs : a0;
-        a1 = a1 > ce ? ce : a1;
         int lo = 0, hi = nrc - 1;  // reference contig holding r0
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
@@ -681,34 +694,24 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
                 hi = mid - 1;
         }
         const long long rs = db.ctg_pstart[rcoff + lo], re = rs + db.ctg_len[rcoff + lo] - 1;
-        long long b0 = (long long)c.r0 - k1 - e, b1 = (long long)c.r1 + e;
-        b0 = b0 < rs ? rs : b0;
-        b1 = b1 > re ? re : b1;
-        l_span_q += (double)(a1 - a0 + 1);
-        l_span_r += (double)(b1 - b0 + 1);
+        const long long a0 = (long long)c.q0 - k1, a1 = c.q1, b0 = (long long)c.r0 - k1, b1 = c.r1;
+        const long long room_ql = a0 - cs, room_qr = ce - a1, room_rlo = b0 - rs, room_rhi = re - b1;
+        // an extension stops where either genome runs out; a reverse chain's left query end faces the reference's high end
+        long long el = c.rev ? room_rhi : room_rlo, er = c.rev ? room_rlo : room_rhi;
+        el = el < room_ql ? el : room_ql;
+        er = er < room_qr ? er : room_qr;
+        el = el < e ? el : e;
+        er = er < e ? er : e;
+        el = el < 0 ? 0 : el;
+        er = er < 0 ? 0 : er;
+        l_span_q += (double)(a1 - a0 + 1 + el + er);
+        l_span_r += (double)(b1 - b0 + 1 + el + er);
         l_a += (double)c.n_anchors;
         l_s += (double)c.n_seeds;
     }
     const double t_span_q = block_sum(l_span_q, ctl.red, tid), t_span_r = block_sum(l_span_r, ctl.red, tid);
     const double t_a = block_sum(l_a, ctl.red, tid), t_s = block_sum(l_s, ctl.red, tid);
     const double t_acc = block_sum((double)n_acc_local, ctl.red, tid);
-    __syncthreads();
-    // per-chunk ANI, seed-weighted mean
-    double sw = 0, sx = 0;
-    int used = 0;
-    for (uint32_t ch = tid; ch < nch && !overflow; ch += FIN_THREADS) {
-        const uint32_t A = accA[ch], S = accS[ch];
-        if ((int)S < prm.min_chunk_seeds || A == 0) continue;
-        double ratio = (double)A / (double)S;
-        if (ratio > 1.0) ratio = 1.0;
-        const double x = pow(ratio, 1.0 / (double)K_SEED);
-        sw += (double)S;
-        sx += (double)S * x;
-        used++;
-    }
-    sw = block_sum(sw, ctl.red, tid);
-    sx = block_sum(sx, ctl.red, tid);
-    const double usedd = block_sum((double)used, ctl.red, tid);
     if (tid == 0) {
         PairOut o;
         o.ani = o.ani_raw = -1.0;
@@ -718,11 +721,13 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         o.span_q = (int64_t)t_span_q;
         o.span_r = (int64_t)t_span_r;
         o.n_chains = (int)t_acc;
-        o.n_chunks_used = (int)usedd;
         o.swapped = (int32_t)pi.swapped;
-        o.overflow = overflow;
-        if (usedd > 0 && sw > 0) {
-            const double mean = sx / sw;
+        // the two end anchors of every chain are anchors by construction: left out of both counts (oracle ora_pair)
+        const int64_t a_in = o.n_anchors - 2 * (int64_t)o.n_chains, s_in = o.n_seeds - 2 * (int64_t)o.n_chains;
+        if (a_in > 0 && s_in > 0) {
+            double ratio = (double)a_in / (double)s_in;
+            if (ratio > 1.0) ratio = 1.0;
+            const double mean = pow(ratio, 1.0 / (double)K_SEED);
             o.ani_raw = mean;
             double afq = (double)o.span_q / (double)db.g_total_len[pi.q];
             double afr = (double)o.span_r / (double)db.g_total_len[pi.r];
@@ -768,17 +773,15 @@ __global__ void edge_scatter_kernel(const unsigned long long *__restrict__ pairs
     edges[pos[t]] = e;
 }
 
-// bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors (roofline
-// bytes), and the number of pairs that exceeded a kernel limit (reported as an error, never silently)
+// bookkeeping: sum over pairs of the query genome's seed count and of the chained anchors (roofline bytes)
 __global__ void pair_sums_kernel(const PairInfo *__restrict__ info, const PairOut *__restrict__ po, int64_t n_pairs,
-                                 const uint64_t *__restrict__ g_seed_off, unsigned long long *sums /* [3] */) {
+                                 const uint64_t *__restrict__ g_seed_off, unsigned long long *sums /* [2] */) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sq = 0, an = 0;
     if (t < n_pairs) {
         const uint32_t q = info[t].q;
         sq = g_seed_off[q + 1] - g_seed_off[q];
         an = (unsigned long long)po[t].n_anchors;
-        if (po[t].overflow) atomicAdd(&sums[2], 1ull);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {

@@ -88,8 +88,7 @@ inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t
 
 struct skb_ctx {
     int device = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr, st_a = nullptr, st_b = nullptr;
-    cudaEvent_t ev_anc[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
     std::vector<cudaEvent_t> up_ev;
     skb_params prm;
     std::string err;
@@ -172,7 +171,6 @@ struct skb_ctx {
         a.ovl_num = prm.ovl_num;
         a.ovl_den = prm.ovl_den;
         a.span_ext = prm.span_ext;
-        a.min_chunk_seeds = prm.min_chunk_seeds;
         a.debias_a = prm.debias_a;
         a.debias_g = prm.debias_g;
         return a;
@@ -337,8 +335,8 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     if (n_pairs == 0) return;
     if (n_pairs >= (1ll << 31)) throw CudaFail{"too many surviving pairs in one call"};
     if (!c->ani_attr_set) {
-        CK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(FIN_SMEM_FIXED + 8 * FIN_MAX_CHUNKS)));
+        CK(cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(FIN_BYTES_PER_CAND * MAXP)));
         c->ani_attr_set = true;
     }
     const DbView view = c->view();
@@ -377,16 +375,19 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     CK(cudaStreamSynchronize(c->st));
     uint64_t total_tasks = 0;
     for (uint32_t v : h_nch) total_tasks += v;
-    if (total_tasks >= (1ull << 32)) throw CudaFail{"too many (pair, chunk) tasks in one call"};
-    // Batches of pairs bound the scratch (<= 8 Mi tasks per batch, 24 GiB) and keep a batch's reference tables and
-    // candidates warm in L2 between its kernels; two buffer sets so that SKB_OVERLAP_STREAMS can pipeline them.
+    // task_off is a 32-bit scan and may wrap when a call holds more than 2^32 (pair, chunk) tasks (a single-species set
+    // of ~6,000 genomes): every kernel uses task_off[p] - base within one batch of <= 8 Mi tasks, which is exact
+    // modulo 2^32.
+    // Batches of pairs bound the scratch (<= 8 Mi tasks per batch) and keep a batch's reference tables and
+    // candidates warm in L2 between its kernels.  One in-order stream: running the anchor kernel of batch b+1 beside
+    // chain/finalize of batch b on a second stream was measured slower in every configuration (round 1).
     static const uint64_t want_batches = [] {
         const char *e = std::getenv("SKB_PAIR_BATCHES");
         return (uint64_t)(e ? std::max(1, atoi(e)) : 6);
     }();
     const uint64_t max_tasks =
         std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + want_batches - 1) / want_batches));
-    struct Batch { int64_t p0, p1; uint64_t base, tasks; uint32_t max_nch; };
+    struct Batch { int64_t p0, p1; uint64_t base, tasks; };
     std::vector<Batch> batches;
     {
         int64_t p0 = 0;
@@ -394,110 +395,65 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         while (p0 < n_pairs) {
             uint64_t tasks = 0;
             int64_t p1 = p0;
-            uint32_t max_nch = 0;
-            while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) {
-                max_nch = std::max(max_nch, h_nch[(size_t)p1]);
-                tasks += h_nch[(size_t)p1++];
-            }
-            batches.push_back({p0, p1, base, tasks, max_nch});
+            while (p1 < n_pairs && (p1 == p0 || tasks + h_nch[(size_t)p1] <= max_tasks)) tasks += h_nch[(size_t)p1++];
+            if (tasks >= (1ull << 32)) throw CudaFail{"one pair has more than 2^32 query chunks"};
+            batches.push_back({p0, p1, base, tasks});
             base += tasks;
             p0 = p1;
         }
     }
     uint64_t cap = 1;
-    for (const Batch &bt : batches) cap = std::max(cap, bt.tasks);
-    if (!c->st_a) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&c->st_a, cudaStreamNonBlocking, lo));
-        CK(cudaStreamCreateWithPriority(&c->st_b, cudaStreamNonBlocking, hi));  // the consumer side goes first
-        for (int k = 0; k < 2; k++) {
-            CK(cudaEventCreateWithFlags(&c->ev_anc[k], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&c->ev_free[k], cudaEventDisableTiming));
-        }
-        CK(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    int64_t cap_pairs = 1;
+    for (const Batch &bt : batches) {
+        cap = std::max(cap, bt.tasks);
+        cap_pairs = std::max(cap_pairs, bt.p1 - bt.p0);
     }
-    const char *names[2][8] = {
-        {"ani0.anc", "ani0.res", "ani0.tn", "ani0.desc", "ani0.cands", "ani0.ncand", "ani0.slow", "ani0.next"},
-        {"ani1.anc", "ani1.res", "ani1.tn", "ani1.desc", "ani1.cands", "ani1.ncand", "ani1.slow", "ani1.next"}};
-    // One in-order stream by default.  SKB_OVERLAP_STREAMS=1 runs the anchor kernel of batch b+1 (low priority) next to
-    // chain/finalize of batch b (high priority) on two streams; measured on B200 this is never faster (the consumers
-    // fill the machine, and an anchor kernel that starts beside finalize's large shared-memory carve-out stays slow
-    // for its whole run: 122 ms serial vs 126-143 ms overlapped on config3), so it is kept only as an experiment.
-    static const bool serial = std::getenv("SKB_OVERLAP_STREAMS") == nullptr;
-    const int nbuf = !serial && batches.size() > 1 ? 2 : 1;  // in-order execution reuses one buffer set
-    uint64_t *b_anc[2];
-    uint32_t *b_res[2];
-    uint16_t *b_tn[2];
-    TaskDesc *b_desc[2];
-    Cand *b_cands[2];
-    uint8_t *b_ncand[2], *b_slow[2];
-    uint32_t *b_next[2];  // the anchor kernel's task counter
-    for (int k = 0; k < nbuf; k++) {
-        PoolRef<uint64_t> r0(c->pool[names[k][0]]);
-        PoolRef<uint32_t> r1(c->pool[names[k][1]]);
-        PoolRef<uint16_t> r2(c->pool[names[k][2]]);
-        PoolRef<TaskDesc> r3(c->pool[names[k][3]]);
-        PoolRef<Cand> r4(c->pool[names[k][4]]);
-        PoolRef<uint8_t> r5(c->pool[names[k][5]]);
-        r0.reserve((size_t)cap * MAXA + 2, 0, c->st);
-        r1.reserve((size_t)cap * MAXA, 0, c->st);
-        r2.reserve((size_t)cap, 0, c->st);
-        r3.reserve((size_t)cap, 0, c->st);
-        r4.reserve((size_t)cap * SLOTS, 0, c->st);
-        r5.reserve((size_t)cap, 0, c->st);
-        PoolRef<uint8_t> r6(c->pool[names[k][6]]);
-        r6.reserve((size_t)cap, 0, c->st);
-        b_slow[k] = r6.p;
-        PoolRef<uint32_t> r7(c->pool[names[k][7]]);
-        r7.reserve(1, 0, c->st);
-        b_next[k] = r7.p;
-        b_anc[k] = r0.p;
-        b_res[k] = r1.p;
-        b_tn[k] = r2.p;
-        b_desc[k] = r3.p;
-        b_cands[k] = r4.p;
-        b_ncand[k] = r5.p;
-    }
-    static const int anchor_ctas_per_sm = [] {
-        const char *e = std::getenv("SKB_ANCHOR_CTAS_PER_SM");
-        return e ? std::max(1, atoi(e)) : 3;
-    }();
-    static const bool trace = std::getenv("SKB_TRACE") != nullptr;            // diagnosis: per-kernel timeline on stderr
+    PoolRef<uint64_t> b_anc(c->pool["ani.anc"]);
+    PoolRef<uint32_t> b_res(c->pool["ani.res"]), b_next(c->pool["ani.next"]), b_pair_nc(c->pool["ani.pair_nc"]),
+        b_fctl(c->pool["ani.fin_ctl"]), b_big_list(c->pool["ani.big_list"]), b_big_nc(c->pool["ani.big_nc"]);
+    PoolRef<uint16_t> b_tn(c->pool["ani.tn"]);
+    PoolRef<TaskDesc> b_desc(c->pool["ani.desc"]);
+    PoolRef<Cand> b_cands(c->pool["ani.cands"]);
+    PoolRef<uint8_t> b_ncand(c->pool["ani.ncand"]), b_slow(c->pool["ani.slow"]);
+    b_anc.reserve((size_t)cap * MAXA + 2, 0, c->st);
+    b_res.reserve((size_t)cap * MAXA, 0, c->st);
+    b_tn.reserve((size_t)cap, 0, c->st);
+    b_desc.reserve((size_t)cap, 0, c->st);
+    b_cands.reserve((size_t)cap * SLOTS, 0, c->st);
+    b_ncand.reserve((size_t)cap, 0, c->st);
+    b_slow.reserve((size_t)cap, 0, c->st);
+    b_next.reserve(1, 0, c->st);
+    b_pair_nc.reserve((size_t)cap_pairs, 0, c->st);
+    b_fctl.reserve(2, 0, c->st);
+    b_big_list.reserve((size_t)cap_pairs, 0, c->st);
+    b_big_nc.reserve((size_t)cap_pairs, 0, c->st);
+    static const bool trace = std::getenv("SKB_TRACE") != nullptr;  // diagnosis: per-kernel timeline on stderr
     struct Span { const char *name; size_t batch; cudaEvent_t e0, e1; };
     std::vector<Span> spans;
     cudaEvent_t ev_t0 = nullptr;
-    auto mark = [&](cudaStream_t s) {
+    auto mark = [&]() {
         cudaEvent_t e = nullptr;
         if (trace) {
             CK(cudaEventCreate(&e));
-            CK(cudaEventRecord(e, s));
+            CK(cudaEventRecord(e, c->st));
         }
         return e;
     };
-    if (trace) ev_t0 = mark(c->st);
-    const cudaStream_t st_a = serial ? c->st : c->st_a, st_b = serial ? c->st : c->st_b;
-    CK(cudaEventRecord(c->ev_ready, c->st));
-    CK(cudaStreamWaitEvent(st_a, c->ev_ready, 0));
-    CK(cudaStreamWaitEvent(st_b, c->ev_ready, 0));
+    if (trace) ev_t0 = mark();
     for (size_t bi = 0; bi < batches.size(); bi++) {
         const Batch &bt = batches[bi];
-        const int k = nbuf == 2 ? (int)(bi & 1) : 0;
         const int64_t np = bt.p1 - bt.p0;
         const uint32_t tasks = (uint32_t)bt.tasks, base = (uint32_t)bt.base;
-        if (nbuf == 2 && bi >= 2) CK(cudaStreamWaitEvent(st_a, c->ev_free[k], 0));  // buffer k is free again
+        CK(cudaMemsetAsync(b_fctl.p, 0, 8, c->st));
         if (tasks) {
-            CK(cudaMemsetAsync(b_ncand[k], 0, (size_t)tasks, st_a));
-            CK(cudaMemsetAsync(b_slow[k], 0, (size_t)tasks, st_a));
-            CK(cudaMemsetAsync(b_next[k], 0, 4, st_a));
-            task_setup_kernel<<<nblk(tasks, 256), 256, 0, st_a>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base,
-                                                                     np, tasks, b_desc[k]);
+            CK(cudaMemsetAsync(b_ncand.p, 0, (size_t)tasks, c->st));
+            CK(cudaMemsetAsync(b_slow.p, 0, (size_t)tasks, c->st));
+            CK(cudaMemsetAsync(b_next.p, 0, 4, c->st));
+            task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
+                                                                   tasks, b_desc.p);
             CK(cudaGetLastError());
-            // a persistent grid fed by the task counter; with SKB_OVERLAP_STREAMS only `anchor_ctas_per_sm` CTAs per SM,
-            // so the consumer kernels of the previous batch find free registers next to it
-            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32),
-                                                   !serial && batches.size() > 1 ? (unsigned)c->sm_count * (unsigned)anchor_ctas_per_sm
-                                                                                 : (unsigned)c->sm_count * 32u);
+            // a persistent grid fed by the task counter
+            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
             if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0));
@@ -505,40 +461,70 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                 c->anchor_ev.push_back(e0);
                 c->anchor_ev.push_back(e1);
             }
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], st_a));
-            cudaEvent_t t0 = mark(st_a);
-            anchor_kernel<<<g1, ANC_THREADS, 0, st_a>>>(view, prm, b_desc[k], tasks, b_anc[k], b_tn[k], b_next[k]);
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st));
+            cudaEvent_t t0 = mark();
+            anchor_kernel<<<g1, ANC_THREADS, 0, c->st>>>(view, prm, b_desc.p, tasks, b_anc.p, b_tn.p, b_next.p);
             CK(cudaGetLastError());
-            if (trace) spans.push_back({"anchor", bi, t0, mark(st_a)});
-            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], st_a));
+            if (trace) spans.push_back({"anchor", bi, t0, mark()});
+            CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st));
             c->anchor_ev_used += 2;
-            c->launches += 2;
-        }
-        CK(cudaEventRecord(c->ev_anc[k], st_a));
-        CK(cudaStreamWaitEvent(st_b, c->ev_anc[k], 0));
-        if (tasks) {
-            cudaEvent_t t0 = mark(st_b);
-            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, st_b>>>(prm, tasks, b_anc[k], b_tn[k], b_res[k], b_desc[k],
-                                                                           b_cands[k], b_ncand[k], b_slow[k]);
+            t0 = mark();
+            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_tn.p, b_res.p, b_desc.p,
+                                                                            b_cands.p, b_ncand.p, b_slow.p);
             CK(cudaGetLastError());
-            if (trace) spans.push_back({"chain", bi, t0, mark(st_b)});
+            if (trace) spans.push_back({"chain", bi, t0, mark()});
             const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
-            ends_kernel<<<g3, END_THREADS, 0, st_b>>>(prm, tasks, b_anc[k], b_res[k], b_tn[k], b_desc[k], b_slow[k],
-                                                        b_cands[k], b_ncand[k]);
+            ends_kernel<<<g3, END_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_res.p, b_tn.p, b_desc.p, b_slow.p, b_cands.p,
+                                                       b_ncand.p);
             CK(cudaGetLastError());
-            c->launches += 2;
+            c->launches += 4;
         }
-        cudaEvent_t tf = mark(st_b);
-        // per-chunk accumulators sized for this batch's longest query (more CTAs per SM, more L1 left for neighbours)
-        const size_t fin_smem = FIN_SMEM_FIXED + 8 * (size_t)std::min<uint32_t>(bt.max_nch, FIN_MAX_CHUNKS);
-        finalize_kernel<<<(unsigned)np, FIN_THREADS, fin_smem, st_b>>>(
-            view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_cands[k], b_ncand[k], d_perm.p + bt.p0, d_out);
+        cudaEvent_t tf = mark();
+        // candidates per pair -> size the shared-memory finalize launch for the batch's largest ordinary pair, list the rest
+        pair_ncand_kernel<<<nblk((uint64_t)np, 128), 128, 0, c->st>>>(d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
+                                                                       b_ncand.p, b_pair_nc.p, b_fctl.p, b_big_list.p, b_big_nc.p);
         CK(cudaGetLastError());
-        if (trace) spans.push_back({"finalize", bi, tf, mark(st_b)});
-        c->launches++;
-        CK(cudaEventRecord(c->ev_free[k], st_b));
+        uint32_t fctl[2] = {0, 0};
+        CK(cudaMemcpyAsync(fctl, b_fctl.p, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        uint32_t fcap = 32;
+        while (fcap < fctl[0]) fcap <<= 1;
+        finalize_kernel<false><<<(unsigned)np, FIN_THREADS, FIN_BYTES_PER_CAND * (size_t)fcap, c->st>>>(
+            view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_cands.p, b_ncand.p, b_pair_nc.p,
+            d_perm.p + bt.p0, d_out, fcap, nullptr, nullptr, nullptr, nullptr);
+        CK(cudaGetLastError());
+        c->launches += 2;
+        if (fctl[1]) {  // pairs beyond MAXP candidates: same kernel body on global scratch, one CTA per pair
+            const uint32_t nbig = fctl[1];
+            std::vector<uint32_t> h_nc(nbig), h_cap(nbig);
+            std::vector<unsigned long long> h_off(nbig);
+            CK(cudaMemcpyAsync(h_nc.data(), b_big_nc.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            unsigned long long off = 0;
+            for (uint32_t k = 0; k < nbig; k++) {
+                uint32_t m = 32;
+                while (m < h_nc[k]) m <<= 1;
+                if (m > FIN_IDX_MASK) throw CudaFail{"a pair has more than 2^24 chain candidates"};
+                h_cap[k] = m;
+                h_off[k] = off;
+                off += (unsigned long long)FIN_BYTES_PER_CAND * m;
+                off = (off + 255) & ~255ull;
+            }
+            PoolRef<unsigned char> d_big(c->pool["ani.big_scratch"]);
+            PoolRef<unsigned long long> d_big_off(c->pool["ani.big_off"]);
+            PoolRef<uint32_t> d_big_cap(c->pool["ani.big_cap"]);
+            d_big.reserve((size_t)off + 256, 0, c->st);
+            d_big_off.upload(h_off, c->st);
+            d_big_cap.upload(h_cap, c->st);
+            finalize_kernel<true><<<nbig, FIN_THREADS, 0, c->st>>>(view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
+                                                                 b_cands.p, b_ncand.p, b_pair_nc.p, d_perm.p + bt.p0, d_out, 0,
+                                                                 b_big_list.p, d_big_off.p, d_big_cap.p, d_big.p);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaStreamSynchronize(c->st));  // h_off / h_cap leave scope
+        }
+        if (trace) spans.push_back({"finalize", bi, tf, mark()});
     }
-    for (int k = 0; k < nbuf; k++) CK(cudaStreamWaitEvent(c->st, c->ev_free[k], 0));  // main stream continues after both
     if (trace) {
         CK(cudaStreamSynchronize(c->st));
         for (const Span &sp : spans) {
@@ -560,7 +546,6 @@ struct EdgeRun {
     int64_t n_screened = 0;
     float ms_screen = 0, ms_ani = 0;
     unsigned long long sums[2] = {0, 0};  // sum query seeds, sum anchors
-    int64_t n_overflow = 0;               // pairs beyond a kernel limit
 };
 
 // pairs on device -> ANI -> compacted edges on host
@@ -601,7 +586,6 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
     ne = h3[0];
     run.sums[0] = h3[1];
     run.sums[1] = h3[2];
-    run.n_overflow = (int64_t)h3[3];
     c->last_ms_anchor = 0;
     c->last_anchor_launches = c->anchor_ev_used / 2;
     for (int i = 0; i + 1 < c->anchor_ev_used; i += 2) {
@@ -613,7 +597,7 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
     run.n_edges = (int64_t)ne;
     c->last_dev_edges = d_edges.p;
     c->last_n_edges = (int64_t)ne;
-    if (run.to_host && !run.n_overflow) {
+    if (run.to_host) {
         run.host = (skb_edge *)std::malloc(std::max<size_t>(1, (size_t)ne) * sizeof(skb_edge));
         if (!run.host) throw CudaFail{"host out of memory for edges"};
         if (ne) {
@@ -629,10 +613,6 @@ void pairs_to_edges(skb_ctx *c, unsigned long long *d_pairs, int64_t n_pairs, do
 }
 
 int emit_edges(skb_ctx *c, EdgeRun &run, skb_edge **edges, int64_t *n_edges) {
-    if (run.n_overflow)
-        return fail(c, SKB_ELIMIT, std::to_string(run.n_overflow) +
-                                       " pair(s) exceed the pair-stage limits (more than 4096 chunks in the query genome or more "
-                                       "than 1024 chains with one chain per chunk); no result is returned for this call");
     *n_edges = run.n_edges;
     if (edges) *edges = run.host;
     return SKB_OK;
@@ -654,13 +634,12 @@ void skb_default_params(skb_params *p) {
     p->min_anchors = 3;
     p->min_score = 45;
     p->max_mult = 8;
-    p->max_chunk_chains = 4;
+    p->max_chunk_chains = 8;
     p->ovl_num = 1;
     p->ovl_den = 2;
-    p->span_ext = 150;
-    p->min_chunk_seeds = 1;
-    p->debias_a = 1.49745019;
-    p->debias_g = 0.8781001;
+    p->span_ext = 170;
+    p->debias_a = 1.438713;
+    p->debias_g = 0.905292;
 }
 
 int skb_create(int32_t device, const skb_params *params, skb_ctx **out) {
@@ -721,15 +700,6 @@ void skb_destroy(skb_ctx *ctx) {
     for (cudaEvent_t e : ctx->anchor_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->up_ev) cudaEventDestroy(e);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
-    if (ctx->st_a) {
-        cudaStreamDestroy(ctx->st_a);
-        cudaStreamDestroy(ctx->st_b);
-        for (int k = 0; k < 2; k++) {
-            cudaEventDestroy(ctx->ev_anc[k]);
-            cudaEventDestroy(ctx->ev_free[k]);
-        }
-        cudaEventDestroy(ctx->ev_ready);
-    }
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->st) {
@@ -1406,9 +1376,7 @@ int skb_pairs_detail(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64_t
             d.span_q = o.span_q;
             d.span_r = o.span_r;
             d.n_chains = o.n_chains;
-            d.n_chunks_used = o.n_chunks_used;
             d.swapped = o.swapped;
-            d.overflow = o.overflow;
         }
         return SKB_OK;
     });

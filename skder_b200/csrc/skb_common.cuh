@@ -90,7 +90,7 @@ struct DbView {
 struct PairOut {
     double ani, ani_raw, af_q, af_r;
     int64_t n_anchors, n_seeds, span_q, span_r;
-    int32_t n_chains, n_chunks_used, swapped, overflow;
+    int32_t n_chains, swapped;
 };
 
 }  // namespace skb

@@ -26,7 +26,7 @@ def test_header_symbols_exported(built_lib):
     for name in declared:
         assert hasattr(L, name), name
     # structure layouts the Python side mirrors
-    assert C.sizeof(_lib.Edge) == 32 and C.sizeof(_lib.PairDetail) == 88 and C.sizeof(_lib.Stats) == 72
+    assert C.sizeof(_lib.Edge) == 32 and C.sizeof(_lib.PairDetail) == 80 and C.sizeof(_lib.Stats) == 72
 
 
 def test_no_cpu_fallback_when_gpu_missing(built_lib):

@@ -105,9 +105,10 @@ def test_triangle_7_against_golden(oracle, sk7, genomes7):
         d_ani.append(r.ani * 100 - g[0])
         d_af += [afa * 100 - g[1], afb * 100 - g[2]]
     d_ani, d_af = np.array(d_ani), np.array(d_af)
-    # documented residuals (ORACLE_VS_GOLDEN.md): ANI sd 0.17 pp, AF sd 1.3 pp
-    assert abs(d_ani.mean()) < 0.12 and d_ani.std() < 0.25 and np.abs(d_ani).max() < 0.7
-    assert abs(d_af.mean()) < 1.0 and d_af.std() < 2.5 and np.abs(d_af).max() < 8.5
+    # documented residuals (ORACLE_VS_GOLDEN.md): ANI sd 0.15 pp, AF sd 0.44 pp -- regression guards, NOT the north
+    # star's 0.05 / 0.5 pp (unreachable without skani's learned model, see the doc)
+    assert abs(d_ani.mean()) < 0.12 and d_ani.std() < 0.25 and np.abs(d_ani).max() < 0.6
+    assert abs(d_af.mean()) < 0.5 and d_af.std() < 0.8 and np.abs(d_af).max() < 2.0
 
 
 def test_triangle_34_against_golden(oracle, genomes34):
@@ -126,9 +127,11 @@ def test_triangle_34_against_golden(oracle, genomes34):
         d_ani.append(r.ani * 100 - g[0])
         d_af += [afa * 100 - g[1], afb * 100 - g[2]]
     d_ani, d_af = np.array(d_ani), np.array(d_af)
-    assert abs(d_ani.mean()) < 0.05 and d_ani.std() < 0.20 and np.abs(d_ani).max() < 0.75
-    assert abs(d_af.mean()) < 0.6 and d_af.std() < 1.7 and np.abs(d_af).max() < 9.0
-    assert (np.abs(d_ani) <= 0.1).mean() > 0.40  # golden's own cross-version drift is 0.15 pp
+    # regression guards at the documented residuals (ORACLE_VS_GOLDEN.md, in fold: ANI sd 0.147 / max 0.52, AF sd 0.44 / max 1.39)
+    assert abs(d_ani.mean()) < 0.03 and d_ani.std() < 0.16 and np.abs(d_ani).max() < 0.60
+    assert abs(d_af.mean()) < 0.1 and d_af.std() < 0.5 and np.abs(d_af).max() < 1.6
+    assert (np.abs(d_ani) <= 0.1).mean() > 0.50  # golden's own cross-version drift is 0.15 pp
+    assert (np.abs(d_af) <= 0.5).mean() > 0.70 and (np.abs(d_af) <= 1.0).mean() > 0.95
 
 
 def test_dist_golden_roles_and_values(oracle, genomes7):
@@ -141,7 +144,7 @@ def test_dist_golden_roles_and_values(oracle, genomes7):
         a, b = by[_acc(ref)], by[_acc(qry)]
         r1, r2 = oracle.pair(a, b), oracle.pair(b, a)
         assert r1.ani == r2.ani and r1.af_a == r2.af_b and r1.af_b == r2.af_a  # symmetric
-        assert abs(r1.ani * 100 - ani) < 0.7 and abs(r1.af_a * 100 - af_ref) < 8.5 and abs(r1.af_b * 100 - af_q) < 8.5
+        assert abs(r1.ani * 100 - ani) < 0.6 and abs(r1.af_a * 100 - af_ref) < 2.0 and abs(r1.af_b * 100 - af_q) < 2.0
 
 
 def test_identical_and_unrelated(oracle):
