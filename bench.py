@@ -1,24 +1,31 @@
 #!/usr/bin/env python3
-"""bench.py -- genome pairs/sec for ANI+AF behind skDER's `skani triangle` call site.
+"""bench.py -- genome pairs/sec for ANI+AF behind skDER's `skani` call sites, and dereplication wall time.
 
   python bench.py --gpus N --steps K --warmup W            (ours; one rank per GPU under torchrun for N>1)
   python bench.py --impl reference --steps K --warmup W    (CPU arm: the oracle port on all host threads)
+  python bench.py --workload config2|config3|config3r|config4|config5 ...
 
 A step = one pass of the hot path over one synthetic genome set (BASELINE.json configs):
   value : pairs/s with sketches already resident in HBM (prescreen + ANI/AF + edge gather), device-timed
   e2e   : pairs/s through the C-ABI from packed genomes in pinned HOST memory to edges on the host
           (H2D upload + sketch + index + prescreen + ANI/AF + D2H), every step.
-The workload is the configuration BASELINE.json quotes its metric on (N=5k x 5 Mbp = configs[2], `config3`; it fits one GPU);
-N>1 shards the same triangle's rows
-round-robin over the ranks (no data-path collective; sketches are replicated by NCCL all-gather
-before the timed region of `value`, inside it for `e2e`).
+  derep : wall seconds of the UNMODIFIED reference `skder -d greedy|dynamic` (baseline/_ref) on the same genomes
+          written as FASTA files, with skder_b200/bin/skani first on PATH (N=1, triangle workloads).
+config4 (`low_mem_greedy`) is the search path: a step = the greedy loop of reference src/skDER/skder.py:116-133
+(one `skani search` per not-yet-accounted genome in N50 order) against the resident sketch database.
+The default workload is the configuration BASELINE.json quotes its metric on (N=5k x 5 Mbp = configs[2], `config3`;
+it fits one GPU).  N>1 shards the same triangle's rows over the ranks (no data-path collective; sketches are
+replicated by NCCL all-gather before the timed region of `value`, inside it for `e2e`).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,16 +37,33 @@ sys.path.insert(0, ROOT)
 GREEDY_SCREEN = 89.5  # skDER default: -s (ANI cutoff 99.5 - 10)   reference bin/skder:199-204 (greedy AND dynamic mode;
                       # dynamic lowers --min-af by 20 only together with -n, bin/skder:218-219)
 GREEDY_MIN_AF = 50.0  # skDER default AF cutoff                    reference bin/skder:325-329
-# bounded sample of the workload the CPU arm is timed on (same generator, same clade structure): 400 genomes,
-# 79,800 pairs, 1,800 survivors -- roughly 30 core-seconds of oracle work
-CPU_SAMPLE_CLADES, CPU_SAMPLE_PER_CLADE = 40, 10
+SEARCH_SCREEN, SEARCH_MIN_AF = 80.0, 15.0  # `skani search` defaults: skDER passes neither option (skder.py:119)
+SKDER_ANI, SKDER_AF = 99.5, 50.0           # skDER's default cutoffs (bin/skder:96-97)
+# bounded sample the `cpu_baseline` leg of OUR arm is timed on (same generator): 80 clades x 5 members keeps the
+# workload's survivor fraction (1.0 % vs 0.98 %)
+CPU_SAMPLE_CLADES, CPU_SAMPLE_PER_CLADE = 80, 5
+REF_BUDGET_S = float(os.environ.get("SKB_REF_BUDGET_S", "240"))  # wall budget of the reference arm's timed steps
+
+
+def cfg(name):
+    from skder_b200 import synth
+
+    return synth.CONFIGS[name]
 
 
 def workload_shape(name):
-    from skder_b200 import synth
-
-    nc, per, L, Lhi, *_ = synth.CONFIGS[name]
+    nc, per, L, Lhi, *_ = cfg(name)
     return nc, per, L
+
+
+def workload_name(w):
+    nc, per, L, Lhi, *_ = cfg(w)
+    size = "%.1f Mbp" % (L / 1e6) if Lhi is None else "%.0f-%.0f Mbp" % (L / 1e6, Lhi / 1e6)
+    if w == "config4":
+        return ("%s: %d synthetic %s genomes (%d clades x %d), low_mem_greedy: `skani sketch` once, then the greedy loop of "
+                "`skani search` calls (skani defaults -s 80 --min-af 15), skDER cutoffs 99.5 / 50" % (w, nc * per, size, nc, per))
+    return ("%s: %d synthetic %s genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER default thresholds: greedy and "
+            "dynamic mode both run `skani triangle -s 89.5 --min-af 50 -E`" % (w, nc * per, size, nc, per))
 
 
 class ClockSampler:
@@ -86,24 +110,33 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/skani_oracle.c) -- the reference's skani is not installable here
 # ------------------------------------------------------------------------------------------------
-def cpu_triangle_components(workload, n_clades, per_clade, threads, screen, min_af):
-    """Time the oracle on a bounded sample; returns component costs per unit.  Sketching runs one genome per host
-    thread; the all-vs-all (prescreen of every pair, ANI/AF of the survivors) runs inside the C library on `threads`
-    pthreads (oracle/skani_oracle.c ora_triangle), so no Python per-pair overhead is in the measurement."""
+def cpu_sketch_clades(workload, clades, per_clade, threads):
+    """Oracle sketches of `clades` (ids) x per_clade members; returns (sketches, seconds spent sketching).  Genomes are
+    generated clade by clade (not timed) so the ASCII text of a 5,000-genome workload is never resident at once."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle as O
     from skder_b200 import synth
 
+    sk, t_sketch = [], 0.0
+    with ThreadPoolExecutor(threads) as ex:
+        step = max(1, threads // 4)
+        for c0 in range(0, len(clades), step):
+            gens = [g for cl in ex.map(lambda c: synth.clade_of(workload, c, per_clade), clades[c0:c0 + step]) for g in cl]
+            t0 = time.perf_counter()
+            sk += list(ex.map(O.Sketch.from_contigs, gens))
+            t_sketch += time.perf_counter() - t0
+    return sk, t_sketch
+
+
+def cpu_triangle_components(workload, n_clades, per_clade, threads, screen, min_af):
+    """One CPU pass over n_clades x per_clade genomes of the workload: sketching one genome per host thread, then the
+    all-vs-all (inverted-index prescreen of every pair, ANI/AF of the survivors) inside the C library on `threads`
+    pthreads (oracle/skani_oracle.c ora_triangle) -- no Python per pair."""
+    from oracle import oracle as O
+
     O.build()
-    nc, per, L, Lhi, dlo, dhi, seed = synth.CONFIGS[workload]
-    with ThreadPoolExecutor(threads) as ex:
-        clades = list(ex.map(lambda c: synth.one_clade(c, per_clade, L, seed, dlo, dhi, 300, Lhi), range(n_clades)))
-    gens = [g for cl in clades for g in cl]
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        sk = list(ex.map(O.Sketch.from_contigs, gens))
-    t_sketch = time.perf_counter() - t0
+    sk, t_sketch = cpu_sketch_clades(workload, list(range(n_clades)), per_clade, threads)
     n = len(sk)
     r = O.triangle(sk, screen / 100.0, min_af / 100.0, threads)
     return {"n": n, "pairs": n * (n - 1) // 2, "survivors": r["survivors"], "edges": r["edges"], "t_sketch": t_sketch,
@@ -119,6 +152,34 @@ def cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch):
     return pairs_full / t, t
 
 
+def cpu_search_loop(workload, threads, n_clades, per_clade):
+    """config4 on the CPU: sketch every genome, then the greedy loop of skder.py:116-133 with one oracle `search`
+    (screen + ANI/AF of the query against every database genome, on `threads` pthreads) per representative."""
+    from oracle import oracle as O
+
+    O.build()
+    sk, t_sketch = cpu_sketch_clades(workload, list(range(n_clades)), per_clade, threads)
+    n = len(sk)
+    order = sorted(range(n), key=lambda g: (-n50_of(sk[g].contig_lens()), g))
+    accounted, reps, t0 = set(), 0, time.perf_counter()
+    for g in order:
+        if g in accounted:
+            continue
+        reps += 1
+        for r, ani, af_r, af_q in O.search(sk, g, SEARCH_SCREEN / 100.0, SEARCH_MIN_AF / 100.0, threads):
+            if round(ani * 100, 2) >= SKDER_ANI and round(af_q * 100, 2) >= SKDER_AF:  # skder.py:128 (col 4 = the query's AF)
+                accounted.add(r)
+    return {"n": n, "reps": reps, "t_sketch": t_sketch, "t_loop": time.perf_counter() - t0}
+
+
+def n50_of(lens):
+    lens = np.sort(np.asarray(lens))[::-1]
+    if len(lens) == 0:
+        return 0
+    c = np.cumsum(lens)
+    return int(lens[np.searchsorted(c, int(c[-1] // 2))])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,38 +187,75 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     nc, per, L = workload_shape(args.workload)
     n_full = nc * per
+    if args.workload == "config4":
+        return run_reference_search(args, threads)
     pairs_full = n_full * (n_full - 1) // 2
     surv_full = nc * per * (per - 1) // 2
-    s_clades, s_per = min(nc, CPU_SAMPLE_CLADES), CPU_SAMPLE_PER_CLADE
-    vals = []
-    comp = None
-    for it in range(args.warmup + args.steps):
-        comp = cpu_triangle_components(args.workload, s_clades, s_per, threads, GREEDY_SCREEN, GREEDY_MIN_AF)
-        if it >= args.warmup:
-            vals.append(cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch=True))
-    value = float(np.mean([v for v, _ in vals]))
-    t_full = float(np.mean([t for _, t in vals]))
-    sample = ("%d clades x %d members of %s (%d genomes, %d pairs, %d survive the screen): sketch %.2fs, inverted-index prescreen %.2fs, "
-              "ANI/AF %.2fs on %d threads; per-unit costs scaled to the full workload (%d genomes, %d pairs, %d survivors)"
-              % (s_clades, s_per, args.workload, comp["n"], comp["pairs"], comp["survivors"], comp["t_sketch"],
-                 comp["t_screen"], comp["t_ani"], threads, n_full, pairs_full, surv_full))
+    # warm-up on the bounded sample (threads, page cache, allocator); it is also the cross-check figure
+    sample = None
+    for _ in range(max(1, args.warmup)):
+        sample = cpu_triangle_components(args.workload, min(nc, CPU_SAMPLE_CLADES), CPU_SAMPLE_PER_CLADE, threads, GREEDY_SCREEN,
+                                         GREEDY_MIN_AF)
+    x_value, x_t = cpu_extrapolate(sample, n_full, pairs_full, surv_full, with_sketch=True)
+    # timed: FULL passes over the workload itself, as many of the requested steps as fit the wall budget (>= 1)
+    comps, t_begin = [], time.perf_counter()
+    for it in range(args.steps):
+        comps.append(cpu_triangle_components(args.workload, nc, per, threads, GREEDY_SCREEN, GREEDY_MIN_AF))
+        per_step_wall = (time.perf_counter() - t_begin) / len(comps)
+        if time.perf_counter() - t_begin + per_step_wall > REF_BUDGET_S:
+            break
+    t_steps = [c["t_sketch"] + c["t_screen"] + c["t_ani"] for c in comps]
+    t_full = float(np.mean(t_steps))
+    value = pairs_full / t_full
+    c0 = comps[-1]
+    sample_txt = ("the full workload, %d of the %d requested steps (wall budget %.0f s): %d genomes, %d pairs, %d survive the screen, "
+                  "%d edges; per step: sketch %.2f s, inverted-index prescreen %.2f s, ANI/AF %.2f s on %d threads (genome generation "
+                  "not timed)" % (len(comps), args.steps, REF_BUDGET_S, c0["n"], c0["pairs"], c0["survivors"], c0["edges"],
+                                  float(np.mean([c["t_sketch"] for c in comps])), float(np.mean([c["t_screen"] for c in comps])),
+                                  float(np.mean([c["t_ani"] for c in comps])), threads))
     line = {
         "impl": "reference", "metric": "genome pairs/sec ANI+AF", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "screen": GREEDY_SCREEN, "min_af": GREEDY_MIN_AF,
-                   "note": "oracle-CPU (C port of the published skani method), NOT the skani binary: skani is absent"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "steps": len(comps), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "screen": GREEDY_SCREEN, "min_af": GREEDY_MIN_AF, "pairs": pairs_full,
+                   "pairs_screened": c0["survivors"], "edges": c0["edges"],
+                   "note": "oracle-CPU (C port of the published skani method), NOT the skani binary: skani is absent. "
+                           "Warm-up steps run on a bounded sample; every timed step is the whole workload",
+                   "sample_cross_check": {"genomes": sample["n"], "pairs": sample["pairs"], "survivors": sample["survivors"],
+                                          "extrapolated_value": x_value, "extrapolated_ms_per_step": x_t * 1e3}},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_name(w):
-    nc, per, L = workload_shape(w)
-    return "%s: %d synthetic %.1f Mbp genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER default thresholds: greedy and dynamic mode both run `skani triangle -s 89.5 --min-af 50 -E`" % (
-        w, nc * per, L / 1e6, nc, per)
+def run_reference_search(args, threads):
+    nc, per, L = workload_shape(args.workload)
+    s_clades = min(nc, int(os.environ.get("SKB_REF_SEARCH_CLADES", "20")))
+    r = None
+    for _ in range(max(1, min(args.warmup, 1)) + 1):
+        r = cpu_search_loop(args.workload, threads, s_clades, per)
+    # searches scale with representatives x database size: R ~ clades, each search touches N genomes' markers and
+    # ~per same-clade survivors
+    n_full = nc * per
+    t_search = r["t_loop"] / r["reps"]
+    t_full = r["t_sketch"] / r["n"] * n_full + (r["reps"] / s_clades * nc) * t_search * (n_full / r["n"])
+    pairs = (r["reps"] / s_clades * nc) * n_full
+    line = {
+        "impl": "reference", "metric": "genome pairs/sec ANI+AF (search path)", "value": pairs / t_full, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": 1, "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload),
+                   "note": "oracle-CPU, NOT skani; EXTRAPOLATED from %d clades x %d (%d genomes, %d searches, %.2f s sketch + "
+                           "%.2f s loop): sketching scales with genomes, the loop with representatives x database size"
+                           % (s_clades, per, r["n"], r["reps"], r["t_sketch"], r["t_loop"])},
+        "cpu_baseline": {"value": pairs / t_full, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": "%d clades x %d of %s, extrapolated" % (s_clades, per, args.workload)},
+        "e2e": {"value": pairs / t_full, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,11 +284,121 @@ def pinned_views(packed, torch):
     return pin, views, keep, total * 8
 
 
+def canonical_edges(edges, canon):
+    """Edge records -> sorted text rows keyed by workload-wide genome numbers (clade * per + member), whatever order
+    the ranks ingested them in; sha256 of that text is the same for every N if the results are."""
+    a, b = canon[edges["a"]], canon[edges["b"]]
+    sw = a > b
+    lo, hi = np.where(sw, b, a), np.where(sw, a, b)
+    af_lo, af_hi = np.where(sw, edges["af_b"], edges["af_a"]), np.where(sw, edges["af_a"], edges["af_b"])
+    order = np.lexsort((hi, lo))
+    h = hashlib.sha256()
+    for i in order:
+        h.update(b"%d\t%d\t%.2f\t%.2f\t%.2f\n" % (lo[i], hi[i], edges["ani"][i], af_lo[i], af_hi[i]))
+    return h.hexdigest()
+
+
+def parity_sample(workload, edges, per, n_clades_checked, n_each, threads, screen, min_af):
+    """Outside every timed region: oracle verdicts for >= n_each pairs the GPU kept and >= n_each pairs it rejected, drawn
+    from n_clades_checked whole clades of the bench's own workload (N=1: genome id = clade * per + member)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(12345)
+    nc = workload_shape(workload)[0]
+    clades = sorted(rng.choice(nc, size=min(nc, n_clades_checked), replace=False).tolist())
+    sk, _ = cpu_sketch_clades(workload, clades, per, threads)
+    gid = {c * per + m: sk[k * per + m] for k, c in enumerate(clades) for m in range(per)}
+    ids = np.array(sorted(gid))
+    have = {(int(e["a"]), int(e["b"])): e for e in edges if int(e["a"]) in gid and int(e["b"]) in gid}
+    kept = sorted(have)
+    kept = [kept[i] for i in rng.choice(len(kept), size=min(n_each, len(kept)), replace=False)] if kept else []
+    rejected = set()
+    while len(rejected) < n_each and len(ids) > 1:
+        a, b = sorted(rng.choice(ids, size=2, replace=False).tolist())
+        if (a, b) not in have:
+            rejected.add((a, b))
+    rejected = sorted(rejected)
+
+    def check_kept(ab):
+        a, b = ab
+        r = O.pair(gid[a], gid[b])
+        ok = O.screen(gid[a], gid[b], screen / 100.0)[1] and r.ani >= 0 and max(r.af_a, r.af_b) * 100 >= min_af
+        e = have[ab]
+        return ok and ("%.2f %.2f %.2f" % (r.ani * 100, r.af_a * 100, r.af_b * 100)) == ("%.2f %.2f %.2f" % (e["ani"], e["af_a"], e["af_b"]))
+
+    def check_rejected(ab):
+        a, b = ab
+        if not O.screen(gid[a], gid[b], screen / 100.0)[1]:
+            return True
+        r = O.pair(gid[a], gid[b])
+        return r.ani < 0 or max(r.af_a, r.af_b) * 100 < min_af
+
+    with ThreadPoolExecutor(threads) as ex:
+        bad = sum(not x for x in ex.map(check_kept, kept)) + sum(not x for x in ex.map(check_rejected, rejected))
+    return {"n_kept_checked": len(kept), "n_rejected_checked": len(rejected), "clades": len(clades), "mismatch": int(bad),
+            "checked_against": "oracle.pair / oracle.screen on the same genomes, 2-decimal rows equal"}
+
+
+def _write_clade_fasta(job):
+    workload, c, per, outdir = job
+    from skder_b200 import synth
+
+    for m, contigs in enumerate(synth.clade_of(workload, c, per)):
+        synth.write_fasta(os.path.join(outdir, "clade%03d_member%03d.fasta" % (c, m)), contigs, name="c%d_m%d" % (c, m))
+    return per
+
+
+def derep_wall(workload, mode, threads, n_clades=None):
+    """`skder -d <mode>` -- the UNMODIFIED reference from baseline/_ref (tools/ref_runner.py) -- on the workload's genomes
+    written as FASTA, with skder_b200/bin/skani first on PATH.  Returns a dict with wall seconds and the reference's own
+    phase log; the FASTA files are generated and written before the clock starts."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_runner
+
+    if ref_runner.reference_tree() is None:
+        return {"unavailable": "baseline/_ref not installed (tools/install_reference.py needs /root/reference once)"}
+    nc, per, L = workload_shape(workload)
+    nc = n_clades or nc
+    need = nc * per * L * 1.02
+    base = os.environ.get("SKB_BENCH_TMP")
+    if not base:
+        cands = [d for d in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(d) and shutil.disk_usage(d).free > 1.5 * need]
+        if not cands:
+            return {"unavailable": "no scratch space for %.0f GB of FASTA" % (need / 1e9)}
+        base = cands[0]
+    work = tempfile.mkdtemp(prefix="skb_derep_", dir=base)
+    try:
+        gdir = os.path.join(work, "genomes")
+        os.makedirs(gdir)
+        t0 = time.perf_counter()
+        with ProcessPoolExecutor(min(threads, 32)) as ex:
+            n = sum(ex.map(_write_clade_fasta, [(workload, c, per, gdir) for c in range(nc)]))
+        t_write = time.perf_counter() - t0
+        out = {"genomes": n, "fasta_dir": base, "fasta_gb": sum(os.path.getsize(os.path.join(gdir, f)) for f in os.listdir(gdir)) / 1e9,
+               "setup_write_s": t_write, "threads": threads, "mode": mode,
+               "command": "skder -g DIR -o OUT -d %s -c %d   (defaults: -i 99.5 -f 50)" % (mode, threads)}
+        wall, reps, outdir = ref_runner.run_skder(gdir + "/", os.path.join(work, "out"), mode, SKDER_ANI, SKDER_AF, threads=threads,
+                                                  env_extra={"SKB_PHASE_LOG": "1"}, timeout=3600)
+        out.update({"wall_s": wall, "representatives": len(reps), "reference_phases_s": ref_runner.phases_from_log(outdir)})
+        log = os.path.join(outdir, "Skani_Triangle_Edge_Output.txt.skani_b200.phases.json")
+        if os.path.exists(log):
+            out["shim_phases_s"] = json.load(open(log))
+        return out
+    except Exception as e:  # the throughput line must not be lost to a dereplication problem
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[-600:])}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from skder_b200 import _lib, build, engine, synth
+    from skder_b200 import _lib, build, engine, multi, synth
 
     build.build()
     rank = int(os.environ.get("RANK", "0"))
@@ -203,23 +411,21 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload == "config4":
+        return run_ours_search(args, torch, dist, rank, world, local)
 
     nc, per, L = workload_shape(args.workload)
     n_full = nc * per
     pairs_full = n_full * (n_full - 1) // 2
     # every rank ingests its share of the clades (rank r: clades r, r+world, ...)
-    from skder_b200 import multi
+    from concurrent.futures import ThreadPoolExecutor
 
     t_gen = time.perf_counter()
     my_clades = list(range(rank, nc, world))
     packed = []
-    # clade-parallel generation on host threads
-    from concurrent.futures import ThreadPoolExecutor
-
-    ncfg = synth.CONFIGS[args.workload]
 
     def gen(c):
-        return [engine.pack_contigs(g) for g in synth.one_clade(c, per, ncfg[2], ncfg[6], ncfg[4], ncfg[5], 300, ncfg[3])]
+        return [engine.pack_contigs(g) for g in synth.clade_of(args.workload, c)]
 
     with ThreadPoolExecutor(max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))) as ex:
         for clade in ex.map(gen, my_clades):
@@ -228,10 +434,11 @@ def run_ours(args):
     pin, views, keep, h2d_bytes = pinned_views(packed, torch)
     del packed
     arr = (C.POINTER(_lib.Packed) * len(views))(*[C.pointer(v) for v in views])
+    # workload-wide genome number of every id after replication (rank-major order)
+    canon = np.array([c * per + m for r in range(world) for c in range(r, nc, world) for m in range(per)], np.int64)
 
     eng = engine.Engine(local)
     L_ = eng._L
-
     phase_ms = []  # (add, replicate, index) wall ms of every sketch_all() call on this rank
 
     def sketch_all():
@@ -282,6 +489,10 @@ def run_ours(args):
             d2h += edges.nbytes
         barrier()
         t_e2e = time.perf_counter() - t0
+    # ---- index build alone, device-timed (reported beside `value`, which starts from the indexed sketch DB)
+    eng.timer_start()
+    eng.index()
+    ms_index_dev = eng.timer_stop()
     # ---- value: sketches resident; device-timed on the library's stream
     l0 = eng.launches
     ms_ani, ms_screen, ms_anchor, n_anchor, st = [], [], [], [], None
@@ -300,9 +511,9 @@ def run_ours(args):
         t_wall = time.perf_counter() - t0
     launches = eng.launches - l0
     if world > 1:
-        tt = torch.tensor([ms_dev, t_e2e, float(np.mean(ms_ani))], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms_dev, t_e2e, float(np.mean(ms_ani)), ms_index_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_dev, t_e2e = float(tt[0]), float(tt[1])
+        ms_dev, t_e2e, ms_index_dev = float(tt[0]), float(tt[1]), float(tt[3])
         cnt = torch.tensor([st.n_pairs_screened, st.sum_query_seeds, st.sum_anchors, launches, h2d_bytes],
                            device="cuda", dtype=torch.int64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -341,19 +552,7 @@ def run_ours(args):
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        comp = cpu_triangle_components(args.workload, min(nc, CPU_SAMPLE_CLADES), CPU_SAMPLE_PER_CLADE, threads, GREEDY_SCREEN,
-                                       GREEDY_MIN_AF)
-        surv_full = nc * per * (per - 1) // 2
-        v, t_full = cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch=False)
-        cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-               "sample": "%d clades x %d members of %s (%d pairs, %d survivors): prescreen run counting %.2fs, ANI/AF %.2fs on "
-                         "%d threads; sketches and the marker index resident (as for `value`); per-unit costs scaled to "
-                         "the full workload" % (min(nc, CPU_SAMPLE_CLADES), CPU_SAMPLE_PER_CLADE, args.workload, comp["pairs"],
-                                                comp["survivors"], comp["t_count"], comp["t_ani"], threads)}
+    threads = os.cpu_count() or 1
     line = {
         "metric": "genome pairs/sec ANI+AF", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -363,7 +562,10 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (sketch DB %.1f GB per rank)" % (
                        (st.sum_query_seeds and (n_full * L / 125 * 8 * 3) / 1e9) or 0.0),
                    "ms_screen": float(np.mean(ms_screen)), "ms_ani": ani_ms, "gen_s": t_gen,
-                   "wall_ms_per_step": t_wall / args.steps * 1e3},
+                   "wall_ms_per_step": t_wall / args.steps * 1e3,
+                   # `value` starts from the indexed sketch DB ("sketches resident on device"); the index
+                   # build (seed tables + inverted marker index) is the prescreen's set-up and is reported here
+                   "ms_index_device": ms_index_dev, "value_incl_index": pairs_full / ((ms_step + ms_index_dev) / 1e3)},
         "clocks": clk.summary(), "clocks_e2e": clk_e2e.summary(),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h // args.steps,
                 "ms_per_step": t_e2e / args.steps * 1e3,
@@ -372,18 +574,148 @@ def run_ours(args):
                 "ms_replicate": float(np.mean([p[1] for p in phase_ms[-args.steps:]])),
                 "ms_index": float(np.mean([p[2] for p in phase_ms[-args.steps:]]))},
         "gpu_launches": launches_all,
+        "edges_sha256": canonical_edges(edges, canon),
         "roofline": {"bound": "hbm", "kernel": "anchor_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                      "ms_per_launch": anchor_ms, "launches_per_step": launches_per_step,
                      "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                     "note": "bound by the L1 data pipe (scattered 32-byte bucket reads) and issue; reference tables are L2-resident; "
-                             "see DESIGN.md section 4"},
+                     "note": "algorithmic (streaming-model) bytes over the kernel's time; the kernel is bound by the L1 data pipe "
+                             "(one scattered 32-byte bucket read per lookup) and issue, its reference tables are L2-resident, "
+                             "so real DRAM traffic (`traffic`) is far below the model; see DESIGN.md section 4"},
         "roofline_stage": {"kernels": "task_setup + anchor + chain + ends + finalize", "algorithmic_bytes": stage_bytes,
                            "ms": ani_ms, "achieved": stage_gbs, "unit": "GB/s", "frac": stage_gbs / peak},
     }
-    if cpu:
-        line["cpu_baseline"] = cpu
+    # ---- outside the timed regions: oracle parity sample of the bench's own edge list, CPU baseline, dereplication
+    if world == 1 and not args.no_parity:
+        line["parity_sample"] = parity_sample(args.workload, edges, per, 12, 600, threads, GREEDY_SCREEN, GREEDY_MIN_AF)
+    if world == 1 and not args.no_cpu:
+        s_nc = min(nc, CPU_SAMPLE_CLADES)
+        comp = cpu_triangle_components(args.workload, s_nc, CPU_SAMPLE_PER_CLADE, threads, GREEDY_SCREEN, GREEDY_MIN_AF)
+        surv_full = nc * per * (per - 1) // 2
+        v, t_full = cpu_extrapolate(comp, n_full, pairs_full, surv_full, with_sketch=False)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "INDICATIVE (oracle port, extrapolated): %d clades x %d members of %s (%d pairs, %d survivors): prescreen run "
+                      "counting %.2fs, ANI/AF %.2fs on %d threads; sketches and the marker index resident (as for `value`); per-unit "
+                      "costs scaled to the full workload.  `bench.py --impl reference` times the whole workload instead"
+                      % (s_nc, CPU_SAMPLE_PER_CLADE, args.workload, comp["pairs"], comp["survivors"], comp["t_count"], comp["t_ani"],
+                         threads)}
+    if world == 1 and args.derep != "off":
+        eng.close()  # the shim opens its own context on this GPU
+        del pin
+        line["derep"] = {m: derep_wall(args.workload, m, threads, n_clades=(10 if args.derep == "sample" else None))
+                         for m in ("greedy", "dynamic")}
+        if "wall_s" in line["derep"]["greedy"]:
+            line["derep_wall_s"] = line["derep"]["greedy"]["wall_s"]
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_ours_search(args, torch, dist, rank, world, local):
+    """config4: `skder -d low_mem_greedy` (reference src/skDER/skder.py:95-134) -- sketch the database once, then the
+    greedy loop: in N50 order, every genome not yet accounted for is searched against the database.  The database is
+    sharded over the ranks (N/P genomes each, no replication); every rank sketches the query itself (that is cheaper
+    than shipping its sketch) and searches its shard; the hits' genome numbers are all-gathered into the accounted set."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from skder_b200 import _lib, engine, synth
+
+    nc, per, L = workload_shape(args.workload)
+    n_full = nc * per
+    t_gen = time.perf_counter()
+
+    def gen(c):
+        return [engine.pack_contigs(g) for g in synth.clade_of(args.workload, c)]
+
+    with ThreadPoolExecutor(max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))) as ex:
+        clades = list(ex.map(gen, range(nc)))  # every rank needs every genome as a potential query
+    packed = [g for cl in clades for g in cl]
+    t_gen = time.perf_counter() - t_gen
+    n50 = np.array([p.n50 for p in packed])
+    order = sorted(range(n_full), key=lambda g: (-int(n50[g]), g))
+    mine = [g for g in range(n_full) if (g // per) % world == rank]  # database shard: whole clades, dealt round-robin
+    my_ids = np.array(mine, np.int64)
+    pin, views, keep, h2d_bytes = pinned_views([packed[g] for g in mine], torch)
+    arr = (C.POINTER(_lib.Packed) * len(views))(*[C.pointer(v) for v in views])
+    eng = engine.Engine(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_run():
+        """sketch + index the shard, then the greedy loop; returns (reps, searches, pairs, t_sketch, t_loop, launches)"""
+        l0 = eng.launches
+        t0 = time.perf_counter()
+        eng.clear()
+        eng._ck(eng._L.skb_add_genomes(eng._h, len(views), arr), "skb_add_genomes")
+        eng.index()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        accounted = np.zeros(n_full, bool)
+        reps = 0
+        for g in order:
+            if accounted[g]:
+                continue
+            reps += 1
+            edges, st = eng.search(packed[g], screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
+            # skder.py:128: ANI >= cutoff and the AF in column 4 (the query's) >= cutoff, on the printed 2-decimal values
+            hit = (np.round(edges["ani"], 2) >= SKDER_ANI) & (np.round(edges["af_b"], 2) >= SKDER_AF)
+            ids = my_ids[edges["a"][hit]]
+            if world > 1:
+                cnt = torch.tensor([len(ids)], device="cuda", dtype=torch.int64)
+                cnts = torch.zeros(world, device="cuda", dtype=torch.int64)
+                dist.all_gather_into_tensor(cnts, cnt)
+                mx = int(cnts.max())
+                send = torch.full((max(mx, 1),), -1, device="cuda", dtype=torch.int64)
+                if len(ids):
+                    send[: len(ids)] = torch.from_numpy(ids).cuda()
+                recv = torch.empty(world * max(mx, 1), device="cuda", dtype=torch.int64)
+                dist.all_gather_into_tensor(recv, send)
+                ids = recv[recv >= 0].cpu().numpy()
+            accounted[ids] = True
+            accounted[g] = True
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return reps, reps, reps * n_full, t1 - t0, t2 - t1, eng.launches - l0
+
+    for _ in range(min(args.warmup, 1)):
+        one_run()
+    res = []
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res.append(one_run())
+        barrier()
+        t_all = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_all], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_all = float(tt[0])
+    if rank == 0:
+        reps, searches, pairs, t_sk, t_loop, launches = res[-1]
+        t_step = t_all / args.steps
+        line = {
+            "metric": "genome pairs/sec ANI+AF (search path)", "value": pairs / float(np.mean([r[4] for r in res])), "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": float(np.mean([r[4] for r in res])) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "representatives": reps, "searches": searches,
+                       "pairs": pairs, "searches_per_s": searches / float(np.mean([r[4] for r in res])),
+                       "ms_sketch_index_db": float(np.mean([r[3] for r in res])) * 1e3, "gen_s": t_gen,
+                       "timing": "host clock between device synchronisations (the loop is sequential host logic around "
+                                 "~%d small launches per search)" % max(1, launches // max(searches, 1)),
+                       "sharding": "database sharded N/P per rank, query sketched on every rank, hit ids all-gathered"},
+            "clocks": clk.summary(),
+            "e2e": {"value": pairs / t_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes * world + sum(
+                packed[g].n_words * 8 for g in order[:1]) * searches), "d2h_bytes_per_step": int(32 * per * searches),
+                    "ms_per_step": t_step * 1e3},
+            "gpu_launches": int(launches * args.steps),
+        }
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -395,8 +727,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", default="config3")
+    ap.add_argument("--workload", default="config3", choices=["tiny", "tinyr", "config2", "config3", "config3r", "config4", "config5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample")
+    ap.add_argument("--derep", choices=["off", "sample", "full"], default=os.environ.get("SKB_BENCH_DEREP", "full"),
+                    help="dereplication wall time through the unmodified reference (N=1): whole workload, 10 clades, or skip")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

@@ -221,6 +221,24 @@ def triangle(sketches, s, min_af, threads, params=None, want_pass=False):
     return out
 
 
+def search(sketches, q, s, min_af, threads, params=None):
+    """One query (index q into `sketches`) against all of them inside the C library: [(ref index, ani, af_ref, af_query)]
+    sorted by ref index; fractions in [0, 1]."""
+    p = params or default_params()
+    n = len(sketches)
+    arr = (C.c_void_p * n)(*[sk.h for sk in sketches])
+    ref = np.zeros(n, np.int32)
+    ani, afr, afq = np.zeros(n), np.zeros(n), np.zeros(n)
+    f = lib().ora_search
+    f.restype = C.c_int64
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p]
+    k = f(arr, n, int(q), float(s), float(min_af), C.byref(p), int(threads), ref.ctypes.data, ani.ctypes.data, afr.ctypes.data,
+          afq.ctypes.data)
+    o = np.argsort(ref[:k])
+    return [(int(ref[i]), float(ani[i]), float(afr[i]), float(afq[i])) for i in o]
+
+
 def pair(a, b, params=None, want_chains=False, max_chains=8192):
     p = params or default_params()
     r = PairResult()

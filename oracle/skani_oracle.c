@@ -743,3 +743,62 @@ int64_t ora_triangle(const ora_sketch_t *const *sk, int n, double screen, double
     free(keys);
     return ns;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * One query against a database on host threads: what `skani search q -d db` computes for one call of the
+ * low_mem_greedy loop (reference src/skDER/skder.py:116-133).  Every database genome is screened against the query
+ * (ora_screen) and, if it passes, compared (ora_pair); rows with an estimate and max(AF) >= min_af are kept.
+ * out_ref / out_ani / out_af_ref / out_af_query need room for n entries.  Returns the number of rows.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const ora_sketch_t *const *sk;
+    int n, q;
+    double screen, min_af;
+    const ora_params_t *p;
+    int64_t next;
+    int32_t *out_ref;
+    double *out_ani, *out_af_ref, *out_af_query;
+    int64_t n_out;
+} search_job_t;
+
+static void *search_worker(void *arg) {
+    search_job_t *j = (search_job_t *)arg;
+    for (;;) {
+        const int64_t r = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (r >= j->n) break;
+        int pass = 0;
+        ora_screen(j->sk[r], j->sk[j->q], j->screen, j->p, &pass);
+        if (!pass) continue;
+        ora_pair_result_t res;
+        ora_pair(j->sk[r], j->sk[j->q], j->p, &res, NULL, 0, NULL);
+        if (res.ani < 0 || (res.af_a < j->min_af && res.af_b < j->min_af)) continue;
+        const int64_t k = __atomic_fetch_add(&j->n_out, 1, __ATOMIC_RELAXED);
+        j->out_ref[k] = (int32_t)r;
+        j->out_ani[k] = res.ani;
+        j->out_af_ref[k] = res.af_a;
+        j->out_af_query[k] = res.af_b;
+    }
+    return NULL;
+}
+
+int64_t ora_search(const ora_sketch_t *const *sk, int n, int q, double screen, double min_af, const ora_params_t *p,
+                   int threads, int32_t *out_ref, double *out_ani, double *out_af_ref, double *out_af_query) {
+    search_job_t j;
+    memset(&j, 0, sizeof(j));
+    j.sk = sk;
+    j.n = n;
+    j.q = q;
+    j.screen = screen;
+    j.min_af = min_af;
+    j.p = p;
+    j.out_ref = out_ref;
+    j.out_ani = out_ani;
+    j.out_af_ref = out_af_ref;
+    j.out_af_query = out_af_query;
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, search_worker, &j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    return j.n_out;
+}

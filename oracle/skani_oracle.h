@@ -113,6 +113,12 @@ int ora_pair(const ora_sketch_t *a, const ora_sketch_t *b, const ora_params_t *p
 int64_t ora_triangle(const ora_sketch_t *const *sk, int n, double screen, double min_af, const ora_params_t *p,
                      int threads, int64_t *n_edges, uint8_t *pass_out, double *t_index, double *t_count, double *t_ani);
 
+/* One query (sk[q]) against all n sketches on `threads` host threads: one `skani search` call of skDER's low_mem_greedy
+ * loop (reference src/skDER/skder.py:119).  Rows (database genome, ANI, AF of the database genome, AF of the query), in
+ * no particular order, for pairs that pass the screen, have an estimate and max(AF) >= min_af.  Returns the row count. */
+int64_t ora_search(const ora_sketch_t *const *sk, int n, int q, double screen, double min_af, const ora_params_t *p,
+                   int threads, int32_t *out_ref, double *out_ani, double *out_af_ref, double *out_af_query);
+
 /* learned-debias substitute: maps raw ANI (+features) to reported ANI */
 double ora_debias(double ani_raw);
 

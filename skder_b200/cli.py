@@ -99,41 +99,82 @@ def write_atomic(path, text):
 def triangle_rows(paths_sorted, names, edges):
     """edges: structured array (a < b, ids index paths_sorted).  Ref = lexicographically smaller path
     (SURVEY.md section 4 fact 3); rows grouped by Ref."""
-    out = []
-    for e in edges:
-        a, b = int(e["a"]), int(e["b"])
-        out.append(fmt_row(paths_sorted[a], paths_sorted[b], e["ani"], e["af_a"], e["af_b"], names[a], names[b]))
-    return out
+    cols = [edges[k].tolist() for k in ("a", "b", "ani", "af_a", "af_b")]  # element access on structured arrays is slow
+    return [fmt_row(paths_sorted[a], paths_sorted[b], ani, afa, afb, names[a], names[b]) for a, b, ani, afa, afb in zip(*cols)]
 
 
 def rect_rows(paths, names, edges):
     """edges: a = reference id, b = query id.  Rows grouped by query, ANI descending."""
-    rows = sorted(((int(e["b"]), -float(e["ani"]), int(e["a"]), e) for e in edges), key=lambda t: t[:3])
-    return [fmt_row(paths[a], paths[b], e["ani"], e["af_a"], e["af_b"], names[a], names[b]) for b, _, a, e in rows]
+    cols = [edges[k].tolist() for k in ("a", "b", "ani", "af_a", "af_b")]
+    rows = sorted(zip(*cols), key=lambda t: (t[1], -t[2], t[0]))
+    return [fmt_row(paths[a], paths[b], ani, afa, afb, names[a], names[b]) for a, b, ani, afa, afb in rows]
 
 
 def _device():
     return int(os.environ.get("SKB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
+INGEST_BATCH = 256  # genomes packed per host batch: batch k+1 is parsed while batch k uploads and is sketched
+
+
+def stream_add(eng, engine_mod, paths, threads, phases=None):
+    """FASTA files -> sketches on the device, streamed: host threads parse and 2-bit pack batch k+1
+    (skb_pack_fasta_many) while the device uploads and sketches batch k (skb_add_genomes), so at most two batches of
+    packed genomes are resident on the host and the ingest hides behind the upload.  Returns the first-record names."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    names, t_wait, t_add = [], 0.0, 0.0
+    mcl = eng.params.min_contig_len
+    with ThreadPoolExecutor(1) as ex:
+        fut = ex.submit(engine_mod.pack_fasta_many, paths[:INGEST_BATCH], threads, mcl) if paths else None
+        for i in range(0, len(paths), INGEST_BATCH):
+            t0 = time.time()
+            packed = fut.result()
+            nxt = paths[i + INGEST_BATCH:i + 2 * INGEST_BATCH]
+            fut = ex.submit(engine_mod.pack_fasta_many, nxt, threads, mcl) if nxt else None
+            t1 = time.time()
+            names += [p.first_name for p in packed]
+            eng.add(packed)
+            del packed
+            t_wait += t1 - t0
+            t_add += time.time() - t1
+    if phases is not None:
+        phases["ingest_wait_s"] = t_wait  # time the device side waited for the parser (first batch + any shortfall)
+        phases["upload_sketch_s"] = t_add
+    return names
+
+
+def _phase_log(opt, phases):
+    if os.environ.get("SKB_PHASE_LOG") == "1":
+        write_atomic(opt["out"].rstrip("/") + ".skani_b200.phases.json", json.dumps(phases))
+
+
 def run_triangle(opt, engine_mod):
+    ph, t0 = {}, time.time()
     paths = sorted(set(read_list(opt["list"])))
     with engine_mod.Engine(_device()) as eng:
-        packed = eng.add_fasta(paths, threads=opt["threads"])
-        names = [p.first_name for p in packed]
-        del packed
+        ph["context_s"] = time.time() - t0
+        names = stream_add(eng, engine_mod, paths, opt["threads"], ph)
+        t1 = time.time()
         eng.index()
+        t2 = time.time()
         edges, st = eng.triangle(screen=opt["screen"], min_af=opt["min_af"])
+        t3 = time.time()
     write_atomic(opt["out"], HEADER + "".join(triangle_rows(paths, names, edges)))
+    ph.update({"index_s": t2 - t1, "triangle_s": t3 - t2, "write_tsv_s": time.time() - t3, "total_s": time.time() - t0,
+               "genomes": len(paths), "edges": int(len(edges))})
+    _phase_log(opt, ph)
     return st
 
 
 def run_sketch(opt, engine_mod):
     paths = read_list(opt["list"])
     os.makedirs(opt["out"], exist_ok=True)
+    from . import daemon
+
+    daemon.stop_for(opt["out"])  # a server still holding the previous contents of this directory must not answer for the new ones
     with engine_mod.Engine(_device()) as eng:
-        packed = eng.add_fasta(paths, threads=opt["threads"])
-        names = [p.first_name for p in packed]
+        names = stream_add(eng, engine_mod, paths, opt["threads"])
         eng.save(opt["out"])
     write_atomic(os.path.join(opt["out"], "manifest.json"), json.dumps({"paths": paths, "names": names}))
 
@@ -142,30 +183,39 @@ def run_search(opt, engine_mod):
     """`skani search q.fa -d DB -o OUT` (reference src/skDER/skder.py:119).  Served by the database's resident
     daemon (skder_b200/daemon.py; started here on first use) unless SKB_NO_DAEMON=1, in which case the database is
     loaded, indexed and searched in this process."""
-    query = opt["positional"][0]
+    # the server runs in another working directory: every path goes over absolute
+    query, db, out = os.path.abspath(opt["positional"][0]), os.path.abspath(opt["db"]), os.path.abspath(opt["out"])
+    opt = dict(opt, db=db, out=out)
     dev = _device()
     if os.environ.get("SKB_NO_DAEMON") != "1":
         import subprocess
 
         from . import daemon
 
-        msg = {"op": "search", "query": query, "screen": opt["screen"], "min_af": opt["min_af"], "out": opt["out"]}
-        rep = daemon.request(opt["db"], dev, msg)
+        msg = {"op": "search", "query": query, "label": opt["positional"][0],  # the row shows the path as it was given
+               "screen": opt["screen"], "min_af": opt["min_af"], "out": out}
+        rep = daemon.request(db, dev, msg)
+        if rep is not None and rep.get("stale"):  # the directory was rewritten under a running server: it has just exited
+            deadline = time.time() + 15.0
+            while time.time() < deadline and daemon.request(db, dev, {"op": "ping"}, timeout=1.0) is not None:
+                time.sleep(0.05)
+            rep = None
         if rep is None:
-            log = open(os.path.join(opt["db"], "skani_b200_daemon.log"), "a")
-            subprocess.Popen([sys.executable, "-m", "skder_b200.daemon", opt["db"], str(dev)], stdout=log, stderr=log,
+            log = open(os.path.join(db, "skani_b200_daemon.log"), "a")
+            subprocess.Popen([sys.executable, "-m", "skder_b200.daemon", db, str(dev)], stdout=log, stderr=log,
                              stdin=subprocess.DEVNULL, start_new_session=True,
                              cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
             deadline = time.time() + float(os.environ.get("SKB_DAEMON_START_TIMEOUT", "600"))
             while rep is None and time.time() < deadline:
                 time.sleep(0.2)
-                if daemon.request(opt["db"], dev, {"op": "ping"}, timeout=5.0):
-                    rep = daemon.request(opt["db"], dev, msg)
+                if daemon.request(db, dev, {"op": "ping"}, timeout=5.0):
+                    rep = daemon.request(db, dev, msg)
         if rep is None:
-            raise RuntimeError("search daemon did not come up (see %s/skani_b200_daemon.log)" % opt["db"])
+            raise RuntimeError("search daemon did not come up (see %s/skani_b200_daemon.log)" % db)
         if not rep.get("ok"):
             raise RuntimeError("search daemon: %s" % rep.get("error"))
         return None
+    query = opt["positional"][0]
     with open(os.path.join(opt["db"], "manifest.json")) as f:
         man = json.load(f)
     paths, names = list(man["paths"]), list(man["names"])
@@ -183,9 +233,7 @@ def run_dist(opt, engine_mod):
     paths = list(dict.fromkeys(refs + queries))
     idx = {p: i for i, p in enumerate(paths)}
     with engine_mod.Engine(_device()) as eng:
-        packed = eng.add_fasta(paths, threads=opt["threads"])
-        names = [p.first_name for p in packed]
-        del packed
+        names = stream_add(eng, engine_mod, paths, opt["threads"])
         eng.index()
         edges, st = eng.rect([idx[p] for p in dict.fromkeys(refs)], [idx[p] for p in dict.fromkeys(queries)],
                              screen=opt["screen"], min_af=opt["min_af"])

@@ -30,6 +30,8 @@ namespace skb {
 
 constexpr int LB = 16;                        // DP look-back in anchors
 constexpr int DP_UNR = 4;                     // anchors per DP iteration (code size vs register moves)
+constexpr int DIAG_SLACK = 64;                // chain_kernel short cut: diagonal drift followed without a rebuild
+constexpr int NEG_F = -(1 << 24);             // DP score of an empty window slot
 constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA pass
 constexpr int DP_THREADS = 128;               // K4b: one task per thread
 constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA pass
@@ -206,7 +208,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     for (int u = 0; u < LB + UNR; u++) {
         Q[u] = 0;
         D[u] = 0;
-        F[u] = -(1 << 24);  // an empty slot can never win
+        F[u] = NEG_F;  // an empty slot can never win
         RC[u] = 0;
     }
     const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
@@ -239,6 +241,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
         }
         if (k == ENDS_K) slow = true;
     };
+    int Mx = NEG_F, Dref = 0;  // short cut state, see below
+    const int diag_lim = prm.max_gap + DIAG_SLACK;
     ulonglong2 vnext[UNR / 2];
 #pragma unroll
     for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap) + x);
@@ -254,12 +258,6 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR) + x);
         }
         uint32_t outp[UNR];
-        // Upper bound on what any predecessor other than the nearest can offer: a candidate is F - gap <= F.  Mx is
-        // the largest F in the window behind the nearest predecessor (it may include one anchor just outside the
-        // window: an over-estimate only costs a missed short cut).
-        int Mx = F[UNR + 1];
-#pragma unroll
-        for (int u = UNR + 2; u < LB + UNR; u++) Mx = max(Mx, F[u]);
 #pragma unroll
         for (int x = 0; x < UNR; x++) {
             const uint64_t a = av[x];
@@ -270,6 +268,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             int best = prm.anchor_score;
             uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
             const int me = UNR - 1 - x;               // this anchor's slot
+            const bool live = i0 + x < my_n;
             auto relax = [&](int sl) {
                 const int dq1 = qi - Q[sl];  // dq - 1
                 const int dd = Di - D[sl];
@@ -282,18 +281,43 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                 }
             };
             relax(me + 1);  // d = 0, the nearest predecessor: ties keep it
-            // Colinear anchors (the usual case) chain onto the nearest predecessor with a score no other one can
-            // reach: when that holds for all 32 tasks of the warp the other 15 predecessors are not looked at.
-            // Same result as the full scan: a later d only replaces `best` with a strictly larger candidate.
-            const bool settled = i0 + x >= my_n || Mx <= best;
+            // Short cut.  Colinear anchors (the usual case) chain onto the nearest predecessor with a score no other
+            // one can reach; then the other 15 are not looked at.  Mx bounds what they can offer: the largest F among
+            // the earlier anchors whose diagonal lies within max_gap + DIAG_SLACK of Dref, where Dref follows this
+            // task's current diagonal to within DIAG_SLACK.  An anchor further off than that is out of max_gap for
+            // this one, and one inside offers F - gap <= Mx: if Mx <= best nothing replaces `best` (a later
+            // predecessor only wins with a strictly larger candidate) -- the same result as the full scan.  When the
+            // diagonal jumps (contig end, indel, rearrangement) Mx is rebuilt for the new diagonal from the window, so
+            // the old chain's high scores do not keep the short cut off for the next 16 anchors.  Stale entries that
+            // have left the window only make Mx too large (a missed short cut).
+            long long dj = (long long)Di - Dref;  // 64-bit: opposite strands are up to 2^32 apart
+            dj = dj < 0 ? -dj : dj;
+            const bool jump = live && dj > DIAG_SLACK;
+            if (__any_sync(0xffffffffu, jump)) {
+                int m2 = NEG_F;
+#pragma unroll
+                for (int d = 1; d < LB; d++) {
+                    int dd = D[me + 1 + d] - Di;
+                    dd = dd < 0 ? -dd : dd;
+                    m2 = max(m2, dd <= diag_lim ? F[me + 1 + d] : NEG_F);
+                }
+                if (jump) {
+                    Mx = m2;
+                    Dref = Di;
+                }
+            }
+            const bool settled = !live || Mx <= best;
             if (!__all_sync(0xffffffffu, settled)) {
 #pragma unroll
                 for (int d = 1; d < LB; d++) relax(me + 1 + d);
             }
-            Mx = max(Mx, F[me + 1]);  // the nearest predecessor is an "other" one for the next anchor
+            {  // the nearest predecessor is an "other" one for the next anchor
+                int dd = D[me + 1] - Dref;
+                dd = dd < 0 ? -dd : dd;
+                Mx = max(Mx, dd <= diag_lim ? F[me + 1] : NEG_F);
+            }
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;
-            const bool live = i0 + x < my_n;
             if (live && best >= prm.min_score && (int)(rci & 0x1ffu) >= prm.min_anchors) {
                 const uint32_t root = rci >> 9;
                 const uint32_t e = ((uint32_t)best << 16) | ((uint32_t)(MAXA - 1 - (i0 + x)) << 8) | root;
@@ -307,7 +331,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             }
             Q[me] = qi + 1;
             D[me] = Di;
-            F[me] = live ? best + prm.anchor_score : -(1 << 24);
+            F[me] = live ? best + prm.anchor_score : NEG_F;
             RC[me] = rci;
         }
         if (i0 < my_n) {

@@ -361,8 +361,34 @@ def test_engine_search_and_daemon(genomes7, oracle, built_lib, tmp_path, monkeyp
             assert subprocess.call([sys.executable, shim, "search", q, "-d", str(db), "-o", str(out), "-t", "2"]) == 0
             assert rows_of(out) == want_rows(q)
         assert daemon.request(str(db), 0, {"op": "ping"}, timeout=5.0)["n"] == 7  # one server answered all three
+        # the socket is private and authenticated: mode 0600 in a 0700 directory, key 0600 inside the database
+        import stat
+
+        sock = daemon.socket_path(str(db), 0)
+        assert stat.S_IMODE(os.stat(sock).st_mode) == 0o600 and stat.S_IMODE(os.stat(os.path.dirname(sock)).st_mode) == 0o700
+        assert stat.S_IMODE(os.stat(daemon._key_path(str(db), 0)).st_mode) == 0o600
+        # a re-run sketches a DIFFERENT genome set into the same directory (skDER reuses its output directory): the next
+        # search must be answered from the new database, never from the resident copy of the old one
+        lst.write_text("".join(p + "\n" for p in genomes7[:5]))
+        assert _run_shim(["sketch", "-l", str(lst), "-o", str(db), "-t", "4"]) == 0
+        out.unlink()
+        assert subprocess.call([sys.executable, shim, "search", genomes7[0], "-d", str(db), "-o", str(out), "-t", "2"]) == 0
+        assert {r[0] for r in rows_of(out)} <= set(genomes7[:5]) and len(rows_of(out)) == 5
+        assert daemon.request(str(db), 0, {"op": "ping"}, timeout=5.0)["n"] == 5
+        # ... and when the files are swapped behind a running server's back (no `skani sketch` of ours involved)
+        import shutil
+
+        other = tmp_path / "db2"
+        lst.write_text("".join(p + "\n" for p in genomes7[2:]))
+        assert _run_shim(["sketch", "-l", str(lst), "-o", str(other), "-t", "4"]) == 0
+        for f in ("sketches.skb", "manifest.json"):
+            shutil.copyfile(other / f, db / (f + ".new"))
+            os.replace(db / (f + ".new"), db / f)
+        out.unlink()
+        assert subprocess.call([sys.executable, shim, "search", genomes7[6], "-d", str(db), "-o", str(out), "-t", "2"]) == 0
+        assert {r[0] for r in rows_of(out)} <= set(genomes7[2:]) and len(rows_of(out)) == 5
     finally:
-        daemon.request(str(db), 0, {"op": "stop"}, timeout=5.0)
+        daemon.stop_for(str(db))
 
 
 def test_many_chains_in_one_chunk(oracle, built_lib):
