@@ -15,7 +15,9 @@ config4 (`low_mem_greedy`) is the search path: a step = the greedy loop of refer
 (one `skani search` per not-yet-accounted genome in N50 order) against the resident sketch database.
 The default workload is the configuration BASELINE.json quotes its metric on (N=5k x 5 Mbp = configs[2], `config3`;
 it fits one GPU).  N>1 shards the same triangle's rows over the ranks (no data-path collective; sketches are
-replicated by NCCL all-gather before the timed region of `value`, inside it for `e2e`).
+replicated by NCCL all-gather before the timed region of `value`, inside it for `e2e`); seed tables are sharded by
+reference genome (each rank builds and probes only its own genomes' tables) and the surviving pairs are exchanged once
+(8 bytes per pair) between the prescreen and the ANI/AF stage.
 """
 import argparse
 import ctypes as C
@@ -383,7 +385,7 @@ def derep_wall(workload, mode, threads, n_clades=None):
                "command": "skder -g DIR -o OUT -d %s -c %d   (defaults: -i 99.5 -f 50)" % (mode, threads)}
         wall, reps, outdir = ref_runner.run_skder(gdir + "/", os.path.join(work, "out"), mode, SKDER_ANI, SKDER_AF, threads=threads,
                                                   env_extra={"SKB_PHASE_LOG": "1"}, timeout=3600)
-        out.update({"wall_s": wall, "representatives": len(reps), "reference_phases_s": ref_runner.phases_from_log(outdir)})
+        out.update({"wall_s": wall, "representatives": len(reps), "reference_phases_s": ref_runner.run_skder.last_phases})
         log = os.path.join(outdir, "Skani_Triangle_Edge_Output.txt.skani_b200.phases.json")
         if os.path.exists(log):
             out["shim_phases_s"] = json.load(open(log))
@@ -447,8 +449,8 @@ def run_ours(args):
         eng.clear()
         eng._ck(L_.skb_add_genomes(eng._h, len(views), arr), "skb_add_genomes")
         t1 = time.perf_counter()
-        if world > 1:
-            multi.replicate_sketches(eng, dist, torch)
+        if world > 1:  # own genomes indexed first (repeat flags travel with the seeds); afterwards this rank owns their tables only
+            multi.replicate_sketches(eng, dist, torch, sharded_index=True)
         t2 = time.perf_counter()
         eng.index()
         t3 = time.perf_counter()
@@ -465,9 +467,13 @@ def run_ours(args):
 
     def triangle():
         t0 = time.perf_counter()
-        edges, st = eng.triangle(GREEDY_SCREEN, GREEDY_MIN_AF, part=rank, n_parts=world, to_host=world == 1)
-        t1 = time.perf_counter()
-        if world > 1:
+        if world == 1:
+            edges, st = eng.triangle(GREEDY_SCREEN, GREEDY_MIN_AF)
+            t1 = time.perf_counter()
+        else:  # rows screened per rank, surviving pairs all-gathered, every pair evaluated by the owner of its reference
+            _, st, st_screen = multi.triangle_sharded(eng, dist, torch, GREEDY_SCREEN, GREEDY_MIN_AF, to_host=False)
+            st.ms_screen = st_screen.ms_screen
+            t1 = time.perf_counter()
             edges = multi.gather_device_edges(eng, dist, torch, sort=False)
         if dbg and rank == 0:
             sys.stderr.write("triangle %.2f ms (screen %.2f ani %.2f) gather %.2f ms\n" % (

@@ -165,13 +165,40 @@ int skb_sketch_view_get(skb_ctx *ctx, skb_sketch_view *view);
  * marker keys are re-tagged with the receiving context's genome ids */
 int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_seeds, int64_t n_seeds,
                         const uint64_t *dev_marker_keys, int64_t n_marker_keys, const uint64_t *host_seed_off,
-                        const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len);
+                        const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len,
+                        int32_t keep_repeat_flags /* 1: the sender ran skb_index, its repeat flags travel with the seeds */);
+
+/* ---- the triangle on several GPUs, sharded by REFERENCE genome (skder_b200/multi.py) ----------
+ * Every context holds all sketches (replicated) but builds seed tables only for the genomes it owns, a contiguous id
+ * range set before skb_index.  The triangle then runs in two steps with one small exchange in between: each rank
+ * screens its rows (skb_screen_triangle leaves the surviving pairs on the device), the pair lists are all-gathered,
+ * and each rank evaluates the pairs whose reference genome -- the one with more seeds -- it owns (skb_pairs_edges with
+ * owned_only).  Every rank therefore probes only tables it built itself, and a reference's pairs stay together on one
+ * GPU (L2 reuse), however the survivors are distributed over the rows. */
+int skb_set_owned(skb_ctx *ctx, int32_t first, int32_t count); /* count = -1: all genomes (the default) */
+int skb_screen_triangle(skb_ctx *ctx, double screen_pct, int32_t part, int32_t n_parts, const uint64_t **dev_pairs,
+                        int64_t *n_pairs, skb_stats *stats);
+/* dev_pairs: (a << 32 | b) on this device; edges may be NULL (result stays on the device, skb_device_edges) */
+int skb_pairs_edges(skb_ctx *ctx, const uint64_t *dev_pairs, int64_t n_pairs, int32_t owned_only, double min_af_pct,
+                    skb_edge **edges, int64_t *n_edges, skb_stats *stats);
 
 /* Device copy of the edge list produced by the last skb_triangle / skb_rect call on this context (same order
  * as the host copy; valid until the next call on the context).  skb_triangle accepts edges == NULL: the result
  * then stays on the device only -- what a multi-GPU caller wants, which gathers the per-rank lists over NCCL
  * (skder_b200/multi.py) instead of bouncing them through host memory. */
 int skb_device_edges(skb_ctx *ctx, const skb_edge **dev_edges, int64_t *n_edges);
+
+/* ---- binary edge hand-off to skDER's greedy selection --------------------------------------
+ * What reference skDERsum (src/skDER/skDERsum.cpp:86-132) computes from the edge TSV: per genome, how many genomes it
+ * covers (connectivity) and which (members, in edge order).  An edge (a, b, ANI, AF_a, AF_b) whose printed ANI is >=
+ * min_ani gives a the member b if the printed AF_b >= min_af, and b the member a if the printed AF_a >= min_af
+ * (skDERsum.cpp:112-124); "printed" = the 2-decimal text skani writes, reproduced exactly on the device.
+ * edges: host array, or NULL for the list the last skb_triangle / skb_rect call left on the device.  Results are
+ * malloc'ed (skb_free): connectivity[n_genomes], member_off[n_genomes + 1], members[member_off[n_genomes]].
+ * The host side (skder_b200/select.py) multiplies by N50 and writes Genome_Information_for_Greedy_Clustering.txt
+ * byte-identical to the reference helper's. */
+int skb_greedy_summary(skb_ctx *ctx, const skb_edge *edges, int64_t n_edges, int32_t n_genomes, double min_ani, double min_af,
+                       int64_t **connectivity, int64_t **member_off, uint32_t **members);
 
 void skb_free(void *p);
 

@@ -114,6 +114,7 @@ struct skb_ctx {
     // built by skb_index
     bool indexed = false;
     int32_t n_indexed = 0;
+    int32_t own_first = 0, own_count = -1;  // genomes whose seed tables this context builds (skb_set_owned); -1: all
     int tab_x2 = 4;        // seed-table buckets per seed, times two: 4 / 2 / 1 = 0.5 / 1 / 2 records per 4-slot bucket
     int tab_x2_forced = 0; // SKB_TAB_X2 (tests exercise the overflow chain with 1)
     DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
@@ -137,6 +138,7 @@ struct skb_ctx {
     DevBuf<uint32_t> d_nch, d_task_off;
 
     int32_t n() const { return (int32_t)h_total_len.size(); }
+    bool owns(int32_t g) const { return own_count < 0 || (g >= own_first && g < own_first + own_count); }
     DbView view() const {
         DbView v;
         v.n_genomes = n_indexed;
@@ -738,6 +740,8 @@ int skb_clear(skb_ctx *ctx) {
         ctx->n_inv_genomes = 0;
         ctx->n_mkeys_indexed = 0;
         ctx->add_calls.clear();
+        ctx->own_first = 0;
+        ctx->own_count = -1;
         ctx->h_tab_off.assign(1, 0);
         ctx->h_tab_buckets.clear();
         ctx->h_ctg_pstart.clear();
@@ -879,8 +883,11 @@ int skb_index(skb_ctx *ctx) {
             const double budget = std::min(0.35 * (double)total_b,
                                            (double)free_b + (double)c->d_tab.cap * 8.0 - 40.0 * (double)(1ull << 30));
             c->tab_x2 = 1;
+            uint64_t own_seeds = 0;
+            for (int32_t g = 0; g < n; g++)
+                if (c->owns(g)) own_seeds += c->h_seed_off[g + 1] - c->h_seed_off[g];
             for (int x2 : {4, 2})
-                if (((double)n_seeds * x2 / 2 + (double)n) * BUCKET * 8.0 <= budget) {
+                if (((double)own_seeds * x2 / 2 + (double)n) * BUCKET * 8.0 <= budget) {
                     c->tab_x2 = x2;
                     break;
                 }
@@ -894,7 +901,8 @@ int skb_index(skb_ctx *ctx) {
         for (int32_t g = 0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
             if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
-            tab_buckets[g] = (uint32_t)std::max<uint64_t>(2, ns * (uint64_t)c->tab_x2 / 2 + 1);
+            // a genome this context does not own is only ever a QUERY here: no table (skb_set_owned)
+            tab_buckets[g] = c->owns(g) ? (uint32_t)std::max<uint64_t>(2, ns * (uint64_t)c->tab_x2 / 2 + 1) : 0u;
             tab_off[g + 1] = tab_off[g] + (uint64_t)tab_buckets[g] * BUCKET;
             uint32_t off = 0;
             for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
@@ -919,16 +927,22 @@ int skb_index(skb_ctx *ctx) {
         c->d_chunk_len.upload(chunk_len, c->st);
         c->d_chunk_off.upload(c->h_chunk_off, c->st);
         // ---- K2: seed hash indices + repeat flags + chunk_begin
-        c->d_tab.reserve(tab_off[n], 0, c->st);
+        c->d_tab.reserve(tab_off[n] + BUCKET, 0, c->st);
         CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
-        if (n_seeds) {
-            tab_insert_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n,
-                                                                    c->d_tab.p, c->d_tab_off.p, c->d_tab_buckets.p, 0);
-            CK(cudaGetLastError());
-            rep_flag_kernel<<<nblk(n_seeds, 256), 256, 0, c->st>>>(c->d_seeds.p, n_seeds, c->d_seed_off.p, n, c->d_tab.p,
-                                                                  c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult, 0);
-            CK(cudaGetLastError());
-            c->launches += 3;
+        {   // the owned genomes are one contiguous id range, so their seeds are one contiguous range too; the repeat
+            // flags of the others arrived with their seeds (skb_import_sketches keeps them)
+            const int32_t o0 = c->own_count < 0 ? 0 : std::min(c->own_first, n);
+            const int32_t o1 = c->own_count < 0 ? n : std::min(c->own_first + c->own_count, n);
+            const uint64_t s0 = c->h_seed_off[o0], s1 = c->h_seed_off[o1];
+            if (s1 > s0) {
+                tab_insert_kernel<<<nblk(s1 - s0, 256), 256, 0, c->st>>>(c->d_seeds.p, s1, c->d_seed_off.p, n, c->d_tab.p,
+                                                                       c->d_tab_off.p, c->d_tab_buckets.p, s0);
+                CK(cudaGetLastError());
+                rep_flag_kernel<<<nblk(s1 - s0, 256), 256, 0, c->st>>>(c->d_seeds.p, s1, c->d_seed_off.p, n, c->d_tab.p,
+                                                                     c->d_tab_off.p, c->d_tab_buckets.p, c->prm.max_mult, s0);
+                CK(cudaGetLastError());
+                c->launches += 3;
+            }
         }
         const uint32_t n_entries = (uint32_t)chunk_start.size() + (uint32_t)n;
         c->d_chunk_begin.reserve(n_entries, 0, c->st);
@@ -1165,83 +1179,216 @@ int skb_get_markers(skb_ctx *ctx, int32_t g, uint64_t *out) {
     });
 }
 
+// Marker prescreen of this partition's rows of the triangle; leaves the surviving pairs (a << 32 | b, a < b, sorted)
+// on the device.  Rows of the dense count matrix are processed in tiles that fit a memory budget, so the matrix
+// never has to hold rows x n counters at once (n = 50,000: 10 GB).
+static int screen_triangle_impl(skb_ctx *c, double screen_pct, int32_t part, int32_t n_parts, unsigned long long **d_out,
+                                int64_t *n_out, int64_t *pairs_total_out) {
+    if (n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
+    if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+    if (c->n_inv_genomes != c->n()) return fail(c, SKB_ESTATE, "query-only genomes present: triangle needs skb_index");
+    const uint32_t n = (uint32_t)c->n_indexed;
+    const uint32_t rows_local = rows_owned(n, (uint32_t)part, (uint32_t)n_parts);
+    int64_t pairs_total = 0;
+    for (uint32_t rl = 0; rl < rows_local; rl++) pairs_total += n - 1 - row_global(rl, (uint32_t)part, (uint32_t)n_parts);
+    if (pairs_total_out) *pairs_total_out = pairs_total;
+    PoolRef<uint32_t> d_cnt(c->pool["skb_triangle.d_cnt"]);
+    PoolRef<unsigned long long> d_pairs(c->pool["skb_triangle.d_pairs"]), d_pairs_sorted(c->pool["skb_triangle.d_pairs_sorted"]), d_np(c->pool["skb_triangle.d_np"]);
+    d_np.reserve(1, 0, c->st);
+    const double scale = screen_pct > 0.0 ? std::pow(screen_pct / 100.0, (double)K_MARKER) : 0.0;
+    static const uint64_t tile_bytes = [] {
+        const char *e = std::getenv("SKB_SCREEN_TILE_MB");
+        return (uint64_t)(e ? std::max(1, atoi(e)) : 2048) << 20;
+    }();
+    const uint32_t tile_rows = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(rows_local, tile_bytes / (4ull * std::max(n, 1u)))) & ~1u;
+    unsigned long long np = 0;
+    std::vector<unsigned long long> tile_np;
+    // pass 1 per tile: count survivors (the count matrix is rebuilt per tile in pass 2; run counting is cheap)
+    for (int pass = 0; pass < 2; pass++) {
+        unsigned long long at = 0;
+        size_t ti = 0;
+        if (pass == 1) {
+            if (!np) break;
+            d_pairs.reserve(np, 0, c->st);
+            d_pairs_sorted.reserve(np, 0, c->st);
+        }
+        for (uint32_t r0 = 0; r0 < rows_local; r0 += tile_rows, ti++) {
+            const uint32_t nr = std::min(tile_rows, rows_local - r0);
+            const uint64_t cells = (uint64_t)nr * n;
+            if (pass == 1 && tile_np[ti] == 0) continue;
+            if (pass == 0 || rows_local > tile_rows) {  // a single tile keeps its counts from pass 0
+                d_cnt.reserve(cells, 0, c->st);
+                if (scale > 0.0) {
+                    CK(cudaMemsetAsync(d_cnt.p, 0, cells * 4, c->st));
+                    if (c->n_inv) {
+                        screen_runs_kernel<<<nblk(c->n_inv, 256), 256, 0, c->st>>>(c->d_inv.p, c->n_inv, d_cnt.p, n, part, n_parts,
+                                                                                  r0, nr);
+                        CK(cudaGetLastError());
+                        c->launches++;
+                    }
+                }
+            }
+            CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
+            screen_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, n, nr, r0, part, n_parts, c->d_marker_cnt.p, scale,
+                                                                      pass ? d_pairs.p + at : nullptr, d_np.p,
+                                                                      pass ? tile_np[ti] : 0ull);
+            CK(cudaGetLastError());
+            c->launches++;
+            if (pass == 0) {
+                unsigned long long t = 0;
+                CK(cudaMemcpyAsync(&t, d_np.p, 8, cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+                tile_np.push_back(t);
+                np += t;
+            } else
+                at += tile_np[ti];
+        }
+    }
+    if (np) sort_keys_u64(c, (const uint64_t *)d_pairs.p, (uint64_t *)d_pairs_sorted.p, np);
+    *d_out = d_pairs_sorted.p;
+    *n_out = (int64_t)np;
+    return SKB_OK;
+}
+
+static void fill_stats(skb_ctx *c, skb_stats *stats, int64_t pairs_total, const EdgeRun &run, float ms01, float ms12,
+                       int64_t launches0) {
+    if (!stats) return;
+    stats->n_pairs_total = pairs_total;
+    stats->n_pairs_screened = run.n_screened;
+    stats->n_edges = run.n_edges;
+    stats->ms_screen = ms01;
+    stats->ms_ani = ms12;
+    stats->ms_total = ms01 + ms12;
+    stats->ms_anchor = c->last_ms_anchor;
+    stats->n_anchor_launches = c->last_anchor_launches;
+    stats->launches = c->launches - launches0;
+    stats->sum_query_seeds = (int64_t)run.sums[0];
+    stats->sum_anchors = (int64_t)run.sums[1];
+}
+
 int skb_triangle(skb_ctx *ctx, double screen_pct, double min_af_pct, int32_t part, int32_t n_parts,
                  skb_edge **edges, int64_t *n_edges, skb_stats *stats) {
     return guarded(ctx, [&]() -> int {
         skb_ctx *c = ctx;
-        if (!n_edges || n_parts < 1 || part < 0 || part >= n_parts) return fail(c, SKB_EINVAL, "bad arguments");
-        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
-        if (c->n_inv_genomes != c->n()) return fail(c, SKB_ESTATE, "query-only genomes present: triangle needs skb_index");
-        const uint32_t n = (uint32_t)c->n_indexed;
+        if (!n_edges) return fail(c, SKB_EINVAL, "bad arguments");
         const int64_t launches0 = c->launches;
         cudaEvent_t e0, e1, e2;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
         CK(cudaEventCreate(&e2));
         CK(cudaEventRecord(e0, c->st));
-        const uint32_t rows_local = rows_owned(n, (uint32_t)part, (uint32_t)n_parts);
-        int64_t pairs_total = 0;
-        for (uint32_t rl = 0; rl < rows_local; rl++) pairs_total += n - 1 - row_global(rl, (uint32_t)part, (uint32_t)n_parts);
-        PoolRef<uint32_t> d_cnt(c->pool["skb_triangle.d_cnt"]);
-        PoolRef<unsigned long long> d_pairs(c->pool["skb_triangle.d_pairs"]), d_pairs_sorted(c->pool["skb_triangle.d_pairs_sorted"]), d_np(c->pool["skb_triangle.d_np"]);
-        d_np.reserve(1, 0, c->st);
-        CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
-        const double scale = screen_pct > 0.0 ? std::pow(screen_pct / 100.0, (double)K_MARKER) : 0.0;
-        const uint64_t cells = (uint64_t)rows_local * n;
-        unsigned long long np = 0;
-        if (cells) {
-            d_cnt.reserve(cells, 0, c->st);
-            if (scale > 0.0) {
-                CK(cudaMemsetAsync(d_cnt.p, 0, cells * 4, c->st));
-                if (c->n_inv) {
-                    screen_runs_kernel<<<nblk(c->n_inv, 256), 256, 0, c->st>>>(c->d_inv.p, c->n_inv, d_cnt.p, n, part,
-                                                                              n_parts);
-                    CK(cudaGetLastError());
-                    c->launches++;
-                }
-            }
-            // two passes over the count matrix: count survivors, then write them
-            screen_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, n, rows_local, part, n_parts,
-                                                                      c->d_marker_cnt.p, scale, nullptr, d_np.p, 0ull);
-            CK(cudaGetLastError());
-            c->launches++;
-            CK(cudaMemcpyAsync(&np, d_np.p, 8, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            if (np) {
-                d_pairs.reserve(np, 0, c->st);
-                d_pairs_sorted.reserve(np, 0, c->st);
-                CK(cudaMemsetAsync(d_np.p, 0, 8, c->st));
-                screen_compact_kernel<<<nblk(cells, 256), 256, 0, c->st>>>(d_cnt.p, n, rows_local, part, n_parts,
-                                                                          c->d_marker_cnt.p, scale, d_pairs.p, d_np.p,
-                                                                          np);
-                CK(cudaGetLastError());
-                c->launches++;
-                sort_keys_u64(c, (const uint64_t *)d_pairs.p, (uint64_t *)d_pairs_sorted.p, np);
-            }
-        }
+        unsigned long long *d_pairs = nullptr;
+        int64_t np = 0, pairs_total = 0;
+        const int rc = screen_triangle_impl(c, screen_pct, part, n_parts, &d_pairs, &np, &pairs_total);
+        if (rc != SKB_OK) return rc;
         EdgeRun run;
         run.to_host = edges != nullptr;
-        run.n_screened = (int64_t)np;
-        pairs_to_edges(c, d_pairs_sorted.p, (int64_t)np, min_af_pct, run, e1, e2);
+        run.n_screened = np;
+        pairs_to_edges(c, d_pairs, np, min_af_pct, run, e1, e2);
         float ms01 = 0, ms12 = 0;
         CK(cudaEventElapsedTime(&ms01, e0, e1));
         CK(cudaEventElapsedTime(&ms12, e1, e2));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         cudaEventDestroy(e2);
+        fill_stats(c, stats, pairs_total, run, ms01, ms12, launches0);
+        return emit_edges(c, run, edges, n_edges);
+    });
+}
+
+// ---- the triangle in two steps, for callers that exchange the surviving pairs between GPUs in between
+// (skder_b200/multi.py: every rank screens its rows, the pair lists are all-gathered, every rank evaluates the pairs
+// whose REFERENCE genome it owns -- the only seed tables it has built, skb_set_owned)
+int skb_set_owned(skb_ctx *ctx, int32_t first, int32_t count) {
+    return guarded(ctx, [&]() -> int {
+        if (first < 0 || count < -1) return fail(ctx, SKB_EINVAL, "bad owned range");
+        ctx->own_first = first;
+        ctx->own_count = count;
+        ctx->indexed = false;
+        return SKB_OK;
+    });
+}
+
+int skb_screen_triangle(skb_ctx *ctx, double screen_pct, int32_t part, int32_t n_parts, const uint64_t **dev_pairs,
+                        int64_t *n_pairs, skb_stats *stats) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!dev_pairs || !n_pairs) return fail(c, SKB_EINVAL, "bad arguments");
+        const int64_t launches0 = c->launches;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, c->st));
+        unsigned long long *d_pairs = nullptr;
+        int64_t np = 0, pairs_total = 0;
+        const int rc = screen_triangle_impl(c, screen_pct, part, n_parts, &d_pairs, &np, &pairs_total);
+        if (rc != SKB_OK) return rc;
+        CK(cudaEventRecord(e1, c->st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *dev_pairs = (const uint64_t *)d_pairs;
+        *n_pairs = np;
         if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
             stats->n_pairs_total = pairs_total;
-            stats->n_pairs_screened = (int64_t)np;
-            stats->n_edges = run.n_edges;
-            stats->ms_screen = ms01;
-            stats->ms_ani = ms12;
-            stats->ms_total = ms01 + ms12;
-            stats->ms_anchor = c->last_ms_anchor;
-            stats->n_anchor_launches = c->last_anchor_launches;
+            stats->n_pairs_screened = np;
+            stats->ms_screen = stats->ms_total = ms;
             stats->launches = c->launches - launches0;
-            stats->sum_query_seeds = (int64_t)run.sums[0];
-            stats->sum_anchors = (int64_t)run.sums[1];
         }
+        return SKB_OK;
+    });
+}
+
+int skb_pairs_edges(skb_ctx *ctx, const uint64_t *dev_pairs, int64_t n_pairs, int32_t owned_only, double min_af_pct,
+                    skb_edge **edges, int64_t *n_edges, skb_stats *stats) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!n_edges || n_pairs < 0 || (n_pairs && !dev_pairs)) return fail(c, SKB_EINVAL, "bad arguments");
+        if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        const int64_t launches0 = c->launches;
+        cudaEvent_t e0, e1, e2;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventCreate(&e2));
+        CK(cudaEventRecord(e0, c->st));
+        unsigned long long *d_pairs = (unsigned long long *)dev_pairs;
+        int64_t np = n_pairs;
+        if (n_pairs && (owned_only || c->own_count >= 0)) {
+            // keep the pairs whose reference genome (more seeds; ties: b) this context owns, order preserved
+            PoolRef<uint32_t> d_f(c->pool["pairs_edges.flag"]), d_p(c->pool["pairs_edges.pos"]);
+            PoolRef<unsigned long long> d_keep(c->pool["pairs_edges.keep"]);
+            d_f.reserve((size_t)n_pairs + 1, 0, c->st);
+            d_p.reserve((size_t)n_pairs + 1, 0, c->st);
+            d_keep.reserve((size_t)n_pairs, 0, c->st);
+            const int32_t o0 = c->own_count < 0 ? 0 : c->own_first, o1 = c->own_count < 0 ? c->n() : c->own_first + c->own_count;
+            pair_owned_flag_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(c->d_seed_off.p, d_pairs, n_pairs, (uint32_t)c->n(),
+                                                                                   (uint32_t)o0, (uint32_t)o1, d_f.p);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_f.p + n_pairs, 0, 4, c->st));
+            exclusive_scan_u32(c, d_f.p, d_p.p, (size_t)n_pairs + 1);
+            pair_keep_kernel<<<nblk((uint64_t)n_pairs, 256), 256, 0, c->st>>>(d_pairs, n_pairs, d_f.p, d_p.p, d_keep.p);
+            CK(cudaGetLastError());
+            uint32_t kept = 0;
+            CK(cudaMemcpyAsync(&kept, d_p.p + n_pairs, 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            c->launches += 2;
+            d_pairs = d_keep.p;
+            np = kept;
+        }
+        EdgeRun run;
+        run.to_host = edges != nullptr;
+        run.n_screened = np;
+        pairs_to_edges(c, d_pairs, np, min_af_pct, run, e1, e2);
+        float ms01 = 0, ms12 = 0;
+        CK(cudaEventElapsedTime(&ms01, e0, e1));
+        CK(cudaEventElapsedTime(&ms12, e1, e2));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaEventDestroy(e2);
+        fill_stats(c, stats, n_pairs, run, ms01, ms12, launches0);
         return emit_edges(c, run, edges, n_edges);
     });
 }
@@ -1253,6 +1400,7 @@ int skb_rect(skb_ctx *ctx, const int32_t *refs, int32_t n_refs, const int32_t *q
         if (!edges || !n_edges || n_refs < 0 || n_queries < 0 || (n_refs && !refs) || (n_queries && !queries))
             return fail(c, SKB_EINVAL, "bad arguments");
         if (!c->indexed || c->n_indexed != c->n()) return fail(c, SKB_ESTATE, "call skb_index first");
+        if (c->own_count >= 0) return fail(c, SKB_ESTATE, "skb_rect on a context that owns only part of the seed tables (skb_set_owned)");
         const int32_t n = c->n_indexed;
         const int64_t launches0 = c->launches;
         std::vector<int32_t> ref_slot(n, -1);
@@ -1353,6 +1501,9 @@ int skb_pairs_detail(skb_ctx *ctx, const uint32_t *a, const uint32_t *b, int64_t
             if (a[i] >= (uint32_t)c->n_indexed || b[i] >= (uint32_t)c->n_indexed || a[i] == b[i])
                 return fail(c, SKB_EINVAL, "pair id out of range");
             hp[(size_t)i] = ((unsigned long long)a[i] << 32) | b[i];
+            const uint64_t nsa = c->h_seed_off[a[i] + 1] - c->h_seed_off[a[i]], nsb = c->h_seed_off[b[i] + 1] - c->h_seed_off[b[i]];
+            if (!c->owns((int32_t)(nsb < nsa ? a[i] : b[i])))
+                return fail(c, SKB_ESTATE, "the reference genome of a pair is not owned by this context (skb_set_owned)");
         }
         PoolRef<unsigned long long> d_pairs(c->pool["skb_pairs_detail.d_pairs"]);
         PoolRef<PairOut> d_out(c->pool["skb_pairs_detail.d_out"]);
@@ -1487,6 +1638,44 @@ int skb_sketch_view_get(skb_ctx *ctx, skb_sketch_view *v) {
     return SKB_OK;
 }
 
+// ---- binary hand-off to skDER's greedy selection -------------------------------------------------------------------
+// The value skDER's consumers see is the 2-decimal TEXT of an edge (`%.2f`, parsed back with stod): thresholds are
+// applied to that, not to the unrounded double.  round2() reproduces it exactly: x * 100 as an error-free product
+// (p + e), round-half-even on the exact value, one correctly rounded division.
+__device__ __forceinline__ double round2(double x) {
+    const double p = x * 100.0, e = fma(x, 100.0, -p);  // x * 100 == p + e exactly
+    double r = floor(p);
+    const double f = p - r;  // exact: p < 2^52
+    if (f > 0.5 || (f == 0.5 && (e > 0.0 || (e == 0.0 && fmod(r, 2.0) != 0.0)))) r += 1.0;
+    else if (f == 0.0 && e < 0.0) {
+        // p is an integer but the exact product lies just below it: the digits after the point are .99999..., which
+        // round back up to p -- nothing to do
+    }
+    return r / 100.0;
+}
+// reference src/skDER/skDERsum.cpp:107-124: an edge (col0 = a, col1 = b, ANI, AF_a, AF_b) with ANI >= min_ani gives
+// genome a the member b if AF_b >= min_af, and genome b the member a if AF_a >= min_af
+__global__ void summary_keys_kernel(const skb_edge *__restrict__ edges, int64_t n, double min_ani, double min_af,
+                                    unsigned long long *__restrict__ keys, unsigned int *__restrict__ conn) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const skb_edge e = edges[i];
+    const bool ok = round2(e.ani) >= min_ani;
+    const bool a_gains = ok && round2(e.af_b) >= min_af, b_gains = ok && round2(e.af_a) >= min_af;
+    keys[2 * i] = a_gains ? ((unsigned long long)e.a << 34) | ((unsigned long long)i << 1) : ~0ull;
+    keys[2 * i + 1] = b_gains ? ((unsigned long long)e.b << 34) | ((unsigned long long)i << 1) | 1ull : ~0ull;
+    if (a_gains) atomicAdd(&conn[e.a], 1u);
+    if (b_gains) atomicAdd(&conn[e.b], 1u);
+}
+__global__ void summary_members_kernel(const skb_edge *__restrict__ edges, const unsigned long long *__restrict__ keys,
+                                       int64_t n_keys, uint32_t *__restrict__ members) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    const unsigned long long key = keys[k];
+    const skb_edge &e = edges[(key & ((1ull << 34) - 1)) >> 1];
+    members[k] = (key & 1ull) ? e.a : e.b;
+}
+
 __global__ void retag_keys_kernel(const uint64_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out,
                                   int64_t gid_delta) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1501,7 +1690,8 @@ __global__ void clear_rep_kernel(const uint64_t *__restrict__ in, uint64_t n, ui
 
 int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_seeds, int64_t n_seeds,
                         const uint64_t *dev_marker_keys, int64_t n_marker_keys, const uint64_t *host_seed_off,
-                        const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len) {
+                        const uint64_t *host_total_len, const uint32_t *host_ctg_off, const uint32_t *host_ctg_len,
+                        int32_t keep_repeat_flags) {
     return guarded(ctx, [&]() -> int {
         skb_ctx *c = ctx;
         if (n_genomes < 0 || n_seeds < 0 || n_marker_keys < 0) return fail(c, SKB_EINVAL, "bad arguments");
@@ -1510,7 +1700,9 @@ int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_see
         const uint64_t cur = c->h_seed_off.back();
         c->d_seeds.reserve(cur + (uint64_t)n_seeds + 1, cur, c->st);
         c->d_mkeys.reserve(c->n_mkeys + (uint64_t)n_marker_keys + 1, c->n_mkeys, c->st);
-        if (n_seeds) {
+        if (n_seeds && keep_repeat_flags)  // the sender indexed its genomes: their repeat flags travel with the seeds
+            CK(cudaMemcpyAsync(c->d_seeds.p + cur, dev_seeds, (size_t)n_seeds * 8, cudaMemcpyDeviceToDevice, c->st));
+        else if (n_seeds) {
             clear_rep_kernel<<<nblk((uint64_t)n_seeds, 256), 256, 0, c->st>>>(dev_seeds, (uint64_t)n_seeds,
                                                                              c->d_seeds.p + cur);
             CK(cudaGetLastError());
@@ -1534,6 +1726,79 @@ int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_see
         }
         c->n_mkeys += (uint64_t)n_marker_keys;
         c->indexed = false;
+        return SKB_OK;
+    });
+}
+
+// Connectivity and member lists of every genome from a BINARY edge list -- what reference skDERsum
+// (src/skDER/skDERsum.cpp:86-132) derives from the TSV through std::map<string, ...>: no path strings, no text parsing.
+int skb_greedy_summary(skb_ctx *ctx, const skb_edge *edges, int64_t n_edges, int32_t n_genomes, double min_ani, double min_af,
+                       int64_t **connectivity, int64_t **member_off, uint32_t **members) {
+    return guarded(ctx, [&]() -> int {
+        skb_ctx *c = ctx;
+        if (!connectivity || !member_off || !members || n_genomes < 0) return fail(c, SKB_EINVAL, "bad arguments");
+        const skb_edge *d_edges = nullptr;
+        if (edges) {
+            if (n_edges < 0) return fail(c, SKB_EINVAL, "bad edge count");
+            for (int64_t i = 0; i < n_edges; i++)
+                if (edges[i].a >= (uint32_t)n_genomes || edges[i].b >= (uint32_t)n_genomes) return fail(c, SKB_EINVAL, "edge id out of range");
+            PoolRef<skb_edge> up(c->pool["greedy_summary.edges"]);
+            up.reserve((size_t)std::max<int64_t>(n_edges, 1), 0, c->st);
+            if (n_edges) CK(cudaMemcpyAsync(up.p, edges, (size_t)n_edges * sizeof(skb_edge), cudaMemcpyHostToDevice, c->st));
+            d_edges = up.p;
+        } else {  // the list the last triangle / rect left on the device
+            d_edges = c->last_dev_edges;
+            n_edges = c->last_n_edges;
+            if (n_genomes < c->n()) return fail(c, SKB_EINVAL, "n_genomes is smaller than the context's genome count");
+        }
+        if (n_edges >= (1ll << 32) || n_genomes >= (1 << GID_BITS)) return fail(c, SKB_ELIMIT, "edge list too large for the summary keys");
+        PoolRef<unsigned long long> d_k(c->pool["greedy_summary.keys"]), d_ks(c->pool["greedy_summary.keys_sorted"]);
+        PoolRef<unsigned int> d_conn(c->pool["greedy_summary.conn"]);
+        PoolRef<uint32_t> d_mem(c->pool["greedy_summary.members"]);
+        const size_t nk = 2 * (size_t)n_edges;
+        d_k.reserve(std::max<size_t>(nk, 1), 0, c->st);
+        d_ks.reserve(std::max<size_t>(nk, 1), 0, c->st);
+        d_conn.reserve((size_t)n_genomes + 1, 0, c->st);
+        d_mem.reserve(std::max<size_t>(nk, 1), 0, c->st);
+        CK(cudaMemsetAsync(d_conn.p, 0, ((size_t)n_genomes + 1) * 4, c->st));
+        std::vector<unsigned int> h_conn((size_t)n_genomes);
+        if (n_edges) {
+            summary_keys_kernel<<<nblk((uint64_t)n_edges, 256), 256, 0, c->st>>>(d_edges, n_edges, min_ani, min_af, d_k.p, d_conn.p);
+            CK(cudaGetLastError());
+            sort_keys_u64(c, (const uint64_t *)d_k.p, (uint64_t *)d_ks.p, nk, 56);  // unused keys (all ones) sort last
+            c->launches++;
+        }
+        if (n_genomes) CK(cudaMemcpyAsync(h_conn.data(), d_conn.p, (size_t)n_genomes * 4, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        int64_t *conn = (int64_t *)std::malloc(sizeof(int64_t) * (size_t)std::max(n_genomes, 1));
+        int64_t *off = (int64_t *)std::malloc(sizeof(int64_t) * ((size_t)n_genomes + 1));
+        if (!conn || !off) {
+            std::free(conn);
+            std::free(off);
+            return fail(c, SKB_ENOMEM, "host out of memory");
+        }
+        off[0] = 0;
+        for (int32_t g = 0; g < n_genomes; g++) {
+            conn[g] = h_conn[(size_t)g];
+            off[g + 1] = off[g] + conn[g];
+        }
+        const int64_t total = off[n_genomes];
+        uint32_t *mem = (uint32_t *)std::malloc(sizeof(uint32_t) * (size_t)std::max<int64_t>(total, 1));
+        if (!mem) {
+            std::free(conn);
+            std::free(off);
+            return fail(c, SKB_ENOMEM, "host out of memory");
+        }
+        if (total) {
+            summary_members_kernel<<<nblk((uint64_t)total, 256), 256, 0, c->st>>>(d_edges, d_ks.p, total, d_mem.p);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaMemcpyAsync(mem, d_mem.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        *connectivity = conn;
+        *member_off = off;
+        *members = mem;
         return SKB_OK;
     });
 }

@@ -86,15 +86,18 @@ __global__ void strip_gid_kernel(uint64_t *keys, uint64_t n) {
 // K3a (triangle): every run of equal markers in the inverted index contributes +1 to each pair of
 // genomes in the run.  Thread i owns entry i and pairs it with the later entries of its run, so
 // row = smaller genome id.  Rows are dealt to partitions in zig-zag order (row_owner, skb_common.cuh).
+// The count matrix holds the partition's local rows [row0, row0 + n_rows) only (row tiles: skb_api.cu).
 __global__ void screen_runs_kernel(const uint64_t *__restrict__ inv, uint64_t n, uint32_t *cnt, uint32_t n_genomes,
-                                   int part, int n_parts) {
+                                   int part, int n_parts, uint32_t row0, uint32_t n_rows) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t k = inv[i];
     const uint32_t gi = (uint32_t)(k & GID_MASK);
     if ((int)row_owner(gi, (uint32_t)n_parts) != part) return;
+    const uint32_t rl = row_local(gi, (uint32_t)n_parts) - row0;  // unsigned: rows before the tile wrap past n_rows
+    if (rl >= n_rows) return;
     const uint64_t m = k >> GID_BITS;
-    uint32_t *row = cnt + (size_t)row_local(gi, (uint32_t)n_parts) * n_genomes;
+    uint32_t *row = cnt + (size_t)rl * n_genomes;
     for (uint64_t j = i + 1; j < n; j++) {
         const uint64_t kj = inv[j];
         if ((kj >> GID_BITS) != m) break;
@@ -104,7 +107,7 @@ __global__ void screen_runs_kernel(const uint64_t *__restrict__ inv, uint64_t n,
 
 // K3b: threshold the count matrix and compact the surviving pairs (a << 32 | b), a < b
 __global__ void screen_compact_kernel(const uint32_t *__restrict__ cnt, uint32_t n_genomes, uint32_t n_rows_local,
-                                      int part, int n_parts, const uint32_t *__restrict__ g_marker_cnt,
+                                      uint32_t row0, int part, int n_parts, const uint32_t *__restrict__ g_marker_cnt,
                                       double cutoff_scale /* screen^21, <=0: everything passes */,
                                       unsigned long long *pairs, unsigned long long *n_pairs,
                                       unsigned long long cap) {
@@ -115,7 +118,7 @@ __global__ void screen_compact_kernel(const uint32_t *__restrict__ cnt, uint32_t
     if (t < total) {
         const uint32_t rl = (uint32_t)(t / n_genomes);
         b = (uint32_t)(t % n_genomes);
-        a = row_global(rl, (uint32_t)part, (uint32_t)n_parts);
+        a = row_global(row0 + rl, (uint32_t)part, (uint32_t)n_parts);
         if (a < n_genomes && b > a) {
             if (cutoff_scale <= 0.0)
                 pass = true;
@@ -199,6 +202,27 @@ __global__ void screen_rect_compact_kernel(const uint32_t *__restrict__ cnt, con
         const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1));
         if (idx < cap) pairs[idx] = ((unsigned long long)a << 32) | b;
     }
+}
+
+// pairs whose reference genome (the one with more seeds; ties: b -- pair_setup_kernel's rule) lies in [own0, own1)
+__global__ void pair_owned_flag_kernel(const uint64_t *__restrict__ g_seed_off, const unsigned long long *__restrict__ pairs,
+                                       int64_t n_pairs, uint32_t n_genomes, uint32_t own0, uint32_t own1,
+                                       uint32_t *__restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const uint32_t a = (uint32_t)(pairs[t] >> 32), b = (uint32_t)(pairs[t] & 0xffffffffu);
+    uint32_t f = 0;
+    if (a < n_genomes && b < n_genomes) {
+        const uint64_t nsa = g_seed_off[a + 1] - g_seed_off[a], nsb = g_seed_off[b + 1] - g_seed_off[b];
+        const uint32_t r = nsb < nsa ? a : b;
+        f = r >= own0 && r < own1;
+    }
+    flag[t] = f;
+}
+__global__ void pair_keep_kernel(const unsigned long long *__restrict__ pairs, int64_t n_pairs, const uint32_t *__restrict__ flag,
+                                 const uint32_t *__restrict__ pos, unsigned long long *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_pairs && flag[t]) out[pos[t]] = pairs[t];
 }
 
 // explicit pair list: |Ma ∩ Mb| by sorted-list intersection, one warp per pair (binary search of

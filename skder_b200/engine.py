@@ -221,6 +221,48 @@ class Engine:
         )
         return (self._take_edges(ptr, n) if to_host else None), st
 
+    def set_owned(self, first, count):
+        """Seed tables are built (next index()) only for genomes first .. first+count-1; count = -1: all."""
+        self._ck(self._L.skb_set_owned(self._h, int(first), int(count)), "skb_set_owned")
+
+    def screen_triangle(self, screen=80.0, part=0, n_parts=1):
+        """Prescreen of this partition's rows; returns (device pointer to the sorted (a << 32 | b) pairs, count, stats)."""
+        ptr, n, st = C.c_void_p(), C.c_int64(), _lib.Stats()
+        self._ck(self._L.skb_screen_triangle(self._h, float(screen), part, n_parts, C.byref(ptr), C.byref(n), C.byref(st)),
+                 "skb_screen_triangle")
+        return int(ptr.value or 0), int(n.value), st
+
+    def pairs_edges(self, dev_pairs, n_pairs, owned_only=True, min_af=15.0, to_host=True):
+        """ANI/AF of a device-resident pair list (only the pairs whose reference this context owns, if owned_only)."""
+        ptr, n, st = C.POINTER(_lib.Edge)(), C.c_int64(), _lib.Stats()
+        self._ck(
+            self._L.skb_pairs_edges(self._h, C.c_void_p(dev_pairs), int(n_pairs), 1 if owned_only else 0, float(min_af),
+                                    C.byref(ptr) if to_host else None, C.byref(n), C.byref(st)),
+            "skb_pairs_edges",
+        )
+        return (self._take_edges(ptr, n) if to_host else None), st
+
+    def greedy_summary(self, edges, n_genomes, min_ani, min_af):
+        """(connectivity[n], member_off[n+1], members[]) of a binary edge list -- reference skDERsum's first pass.
+        edges: EDGE_DTYPE array, or None for the list the last triangle/rect left on the device."""
+        conn, off, mem = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_uint32)()
+        if edges is not None:
+            edges = np.ascontiguousarray(edges, EDGE_DTYPE)
+        self._ck(
+            self._L.skb_greedy_summary(self._h, edges.ctypes.data if edges is not None else None,
+                                       len(edges) if edges is not None else 0, int(n_genomes), float(min_ani), float(min_af),
+                                       C.byref(conn), C.byref(off), C.byref(mem)),
+            "skb_greedy_summary",
+        )
+        try:
+            c = np.ctypeslib.as_array(conn, shape=(max(n_genomes, 1),))[:n_genomes].copy()
+            o = np.ctypeslib.as_array(off, shape=(n_genomes + 1,)).copy()
+            m = np.ctypeslib.as_array(mem, shape=(max(int(o[-1]), 1),))[: int(o[-1])].copy()
+        finally:
+            for p in (conn, off, mem):
+                self._L.skb_free(p)
+        return c, o, m
+
     def device_edges(self):
         """(device pointer, count) of the last triangle/rect result; valid until the next call on this engine."""
         ptr, n = C.c_void_p(), C.c_int64()

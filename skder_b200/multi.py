@@ -25,10 +25,17 @@ def _dev_tensor(torch, ptr, n, device):
     return torch.as_tensor(_DevArray(ptr, n), device=device)
 
 
-def replicate_sketches(eng, dist, torch):
+def replicate_sketches(eng, dist, torch, sharded_index=False):
     """Every rank holds the sketches of its own genomes; afterwards every rank holds all of them,
-    ordered by (rank, local order).  Collective: all ranks must call."""
+    ordered by (rank, local order).  Collective: all ranks must call.
+
+    sharded_index: the rank first indexes its own genomes (their repeat flags are part of the seed records and travel
+    with them) and afterwards owns exactly those genomes (skb_set_owned): the next Engine.index() builds seed tables
+    for them only -- 1/P of the table work and memory per rank -- and triangle_sharded() sends every pair to the rank
+    that owns its reference genome."""
     world, rank = dist.get_world_size(), dist.get_rank()
+    if sharded_index and eng.n_genomes:
+        eng.index()
     device = torch.device("cuda", eng.device)
     v = eng.sketch_view()
     n = v.n_genomes
@@ -39,8 +46,7 @@ def replicate_sketches(eng, dist, torch):
         "ctg_off": np.ctypeslib.as_array(v.host_ctg_off, shape=(n + 1,)).copy(),
         "ctg_len": np.ctypeslib.as_array(v.host_ctg_len, shape=(max(int(v.n_contigs), 1),))[: int(v.n_contigs)].copy(),
     }
-    metas = [None] * world
-    dist.all_gather_object(metas, meta)
+    metas = _exchange_meta(meta, dist, torch, torch.device("cuda", eng.device) if dist.get_backend() == "nccl" else None)
     gathered = []
     for key, ptr, cnt in (("n_seeds", v.dev_seeds, v.n_seeds), ("n_mkeys", v.dev_marker_keys, v.n_marker_keys)):
         mx = max(int(m[key]) for m in metas)
@@ -64,10 +70,68 @@ def replicate_sketches(eng, dist, torch):
             eng._L.skb_import_sketches(
                 eng._h, int(m["n"]), C.c_void_p(seeds.data_ptr() + 8 * r * s_stride), int(m["n_seeds"]),
                 C.c_void_p(mkeys.data_ptr() + 8 * r * m_stride), int(m["n_mkeys"]), so.ctypes.data, tl.ctypes.data,
-                co.ctypes.data, cl.ctypes.data),
+                co.ctypes.data, cl.ctypes.data, 1 if sharded_index else 0),
             "skb_import_sketches",
         )
+    if sharded_index:
+        eng.set_owned(sum(int(m["n"]) for m in metas[:rank]), int(metas[rank]["n"]))
     return metas
+
+
+def _exchange_meta(meta, dist, torch, device):
+    """The per-rank host tables of replicate_sketches as two tensor all-gathers (sizes, then one padded int64 blob)
+    instead of pickled objects: no Python object serialisation in the per-step path."""
+    world = dist.get_world_size()
+    n, nctg = int(meta["n"]), len(meta["ctg_len"])
+    head = torch.tensor([n, int(meta["n_seeds"]), int(meta["n_mkeys"]), nctg], dtype=torch.int64, device=device)
+    heads = torch.zeros(world * 4, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(heads, head)
+    heads = heads.cpu().numpy().reshape(world, 4)
+    size = lambda h: (int(h[0]) + 1) + int(h[0]) + (int(h[0]) + 1) + int(h[3])
+    mx = max(1, max(size(h) for h in heads))
+    blob = np.zeros(mx, np.int64)
+    parts = [np.asarray(meta["seed_off"], np.uint64).view(np.int64), np.asarray(meta["total_len"], np.uint64).view(np.int64),
+             np.asarray(meta["ctg_off"], np.int64), np.asarray(meta["ctg_len"], np.int64)]
+    cat = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+    blob[: len(cat)] = cat
+    send = torch.from_numpy(blob).to(device) if device is not None else torch.from_numpy(blob)
+    recv = torch.zeros(world * mx, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy().reshape(world, mx)
+    out = []
+    for r in range(world):
+        n_r, ns, nm, nc = (int(x) for x in heads[r])
+        o = 0
+        seed_off = recv[r, o:o + n_r + 1].view(np.uint64).copy(); o += n_r + 1
+        total_len = recv[r, o:o + n_r].view(np.uint64).copy(); o += n_r
+        ctg_off = recv[r, o:o + n_r + 1].astype(np.uint32); o += n_r + 1
+        ctg_len = recv[r, o:o + nc].astype(np.uint32)
+        out.append({"n": n_r, "n_seeds": ns, "n_mkeys": nm, "seed_off": seed_off, "total_len": total_len, "ctg_off": ctg_off,
+                    "ctg_len": ctg_len})
+    return out
+
+
+def triangle_sharded(eng, dist, torch, screen, min_af, to_host=False):
+    """The triangle over P ranks, sharded by reference genome (after replicate_sketches(sharded_index=True) + index()):
+    every rank screens its rows, the surviving pair lists (8 bytes per pair) are all-gathered over NCCL, and every rank
+    evaluates the pairs whose reference genome it owns.  Returns (edges or None, stats of the pair stage, stats of the
+    screen); edges are this rank's, sorted by the gathered pair order."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    device = torch.device("cuda", eng.device)
+    ptr, n, st_screen = eng.screen_triangle(screen, part=rank, n_parts=world)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=device))
+    counts = counts.tolist()
+    mx = max(max(counts), 1)
+    send = torch.zeros(mx, dtype=torch.int64, device=device)
+    if n:
+        send[:n].copy_(_dev_tensor(torch, ptr, n, device))
+    recv = torch.empty(world * mx, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    allp = torch.cat([recv[r * mx: r * mx + c] for r, c in enumerate(counts)]) if sum(counts) else recv[:0]
+    torch.cuda.current_stream(device).synchronize()  # the library reads the list on its own stream
+    edges, st = eng.pairs_edges(allp.data_ptr(), int(allp.numel()), owned_only=True, min_af=min_af, to_host=to_host)
+    return edges, st, st_screen
 
 
 def gather_edges(edges, dist, torch, device=None, sort=True):

@@ -112,6 +112,20 @@ def _worker(rank, world, port, q):
         q.put((len(out), [(int(x["a"]), int(x["b"])) for x in out]))
     else:
         assert len(out) == 0
+    # the sketch tables of replicate_sketches travel as padded tensors (no pickled objects); ranks hold different counts
+    n_mine = 3 + 2 * rank
+    meta = {"n": n_mine, "n_seeds": 1000 + rank, "n_mkeys": 77 * (rank + 1),
+            "seed_off": np.arange(n_mine + 1, dtype=np.uint64) * np.uint64(1 << 33),  # beyond 32 bits
+            "total_len": np.arange(n_mine, dtype=np.uint64) + np.uint64(5_000_000 + rank),
+            "ctg_off": np.arange(n_mine + 1, dtype=np.uint32) * 2, "ctg_len": np.arange(2 * n_mine, dtype=np.uint32) + 500}
+    metas = multi._exchange_meta(meta, dist, torch, None)
+    assert len(metas) == world
+    for r, m in enumerate(metas):
+        k = 3 + 2 * r
+        assert m["n"] == k and m["n_seeds"] == 1000 + r and m["n_mkeys"] == 77 * (r + 1)
+        assert np.array_equal(m["seed_off"], np.arange(k + 1, dtype=np.uint64) * np.uint64(1 << 33))
+        assert np.array_equal(m["total_len"], np.arange(k, dtype=np.uint64) + np.uint64(5_000_000 + r))
+        assert np.array_equal(m["ctg_off"], np.arange(k + 1, dtype=np.uint32) * 2) and len(m["ctg_len"]) == 2 * k
     # a rank with nothing to send
     out2 = multi.gather_edges(mine if rank == 0 else np.zeros(0, EDGE_DTYPE), dist, torch)
     if rank == 0:

@@ -503,3 +503,83 @@ def test_fragmented_genome_beyond_the_shared_memory_limits(oracle, built_lib):
         assert det[0].n_chains > 4096 and det[0].swapped == 1  # the fragmented copy is the query
         edges, st = e.triangle(screen=80.0, min_af=15.0)
         assert len(edges) == 3
+
+
+def test_binary_edge_handoff_equals_reference_skdersum(eng7, genomes7, built_lib, tmp_path):
+    """Genome_Information_for_Greedy_Clustering.txt from binary edges (skb_greedy_summary + select.py) is
+    byte-identical to what the reference's own skDERsum prints from the TSV -- on both golden edge lists (ids assigned
+    from their paths) and on this engine's own unrounded edges against its own TSV."""
+    import replay
+    from conftest import GOLDEN
+    from skder_b200 import cli, select
+    from skder_b200.engine import EDGE_DTYPE
+
+    helpers = replay.helpers()
+    if "skDERsum" not in helpers:
+        pytest.skip("reference skDERsum not built")
+    import subprocess
+
+    e, packed = eng7
+    for gdir, cuts in (("skder_results", [(99.0, 50.0), (97.0, 50.0)]), ("skder_gtdb_results", [(99.0, 50.0), (98.0, 90.0), (90.0, 10.0)])):
+        tsv = os.path.join(GOLDEN, gdir, "Skani_Triangle_Edge_Output.txt")
+        n50f = os.path.join(GOLDEN, gdir, "Concatenated_N50.txt")
+        rows = [ln.rstrip("\n").split("\t") for ln in open(tsv).read().splitlines()[1:]]
+        paths = sorted({r[0] for r in rows} | {r[1] for r in rows} | {ln.split("\t")[0] for ln in open(n50f) if ln.strip()})
+        idx = {p: i for i, p in enumerate(paths)}
+        edges = np.array([(idx[r[0]], idx[r[1]], float(r[2]), float(r[3]), float(r[4])) for r in rows], EDGE_DTYPE)
+        n50_rows = [(ln.split("\t")[0], int(ln.split("\t")[1])) for ln in open(n50f) if ln.strip()]
+        for ani, af in cuts:
+            want = subprocess.check_output([helpers["skDERsum"], tsv, n50f, str(ani), str(af)], text=True)
+            assert select.greedy_information(e, edges, paths, n50_rows, ani, af) == want, (gdir, ani, af)
+    # this engine's own result: unrounded doubles on the device vs the 2-decimal text the shim writes
+    paths = sorted(genomes7)
+    edges, _ = e.triangle(screen=80.0, min_af=15.0)
+    names = [p.first_name for p in packed]
+    tsv = tmp_path / "edges.tsv"
+    tsv.write_text(cli.HEADER + "".join(cli.triangle_rows(paths, names, edges)))
+    n50f = tmp_path / "n50.tsv"
+    n50f.write_text("".join("%s\t%d\n" % (p.path, p.n50) for p in packed))
+    n50_rows = [(p.path, p.n50) for p in packed]
+    for ani in (97.0, 98.61, 98.73, 99.02, 99.5):  # cutoffs sitting exactly on printed values of this edge list
+        for af in (50.0, 89.5, 95.04):
+            want = subprocess.check_output([helpers["skDERsum"], str(tsv), str(n50f), str(ani), str(af)], text=True)
+            assert select.greedy_information(e, None, paths, n50_rows, ani, af) == want, (ani, af)  # None: device-resident list
+            assert select.greedy_information(e, edges, paths, n50_rows, ani, af) == want, (ani, af)
+
+
+def test_reference_sharded_triangle_single_process(eng7, ora7, oracle, genomes7, built_lib):
+    """The two-step triangle of the multi-GPU path on one device: contexts that own disjoint id ranges of the same
+    replicated sketch set, each evaluating the pairs whose reference it owns, together reproduce the full triangle."""
+    import ctypes as C
+
+    from skder_b200 import engine
+
+    e, packed = eng7
+    full, _ = e.triangle(screen=80.0, min_af=15.0)
+    for splits in ([(0, 3), (3, 4)], [(0, 1), (1, 2), (3, 4)]):
+        got = []
+        for first, count in splits:
+            with engine.Engine(0) as e2:
+                e2.add(packed)
+                e2.index()  # repeat flags of every genome, as the owning rank would have computed them
+                e2.set_owned(first, count)
+                e2.index()
+                ptr, n, st = e2.screen_triangle(80.0)
+                assert n == 21 and st.n_pairs_screened == 21
+                edges, st2 = e2.pairs_edges(ptr, n, owned_only=True, min_af=15.0)
+                assert st2.n_pairs_screened == len(edges)  # every owned pair of this set becomes an edge
+                got.append(edges)
+                # a pair whose reference lives elsewhere is refused, not answered from a missing table
+                sizes = [e2.sizes(g)["n_seeds"] for g in range(7)]
+                other = [g for g in range(7) if not (first <= g < first + count)]
+                own = [g for g in range(7) if first <= g < first + count]
+                bad = [(a, b) for a in own for b in other if sizes[b] > sizes[a]]
+                if bad:
+                    with pytest.raises(engine.SkbError):
+                        e2.pairs_detail([bad[0][0]], [bad[0][1]])
+        cat = np.sort(np.concatenate(got), order=["a", "b"])
+        covered = sum(c for _, c in splits)
+        if covered == 7:
+            assert np.array_equal(cat, np.sort(full, order=["a", "b"]))
+        else:  # genome 2 is owned by nobody: exactly the pairs with reference 2 are missing
+            assert len(cat) < len(full) and set(map(tuple, cat[["a", "b"]].tolist())) < set(map(tuple, full[["a", "b"]].tolist()))

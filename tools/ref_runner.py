@@ -52,10 +52,11 @@ def run_skder(genome_dir_or_files, outdir, mode="greedy", ani=99.0, af=50.0, thr
     if clusters:
         cmd.append("-n")
     cmd += list(extra)
-    t0 = time.perf_counter()
+    t0, w0 = time.perf_counter(), time.time()
     p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
     wall = time.perf_counter() - t0
     out = outdir if outdir.endswith("/") else outdir + "/"
+    run_skder.last_phases = phases_from_files(out, w0, time.time())
     res = os.path.join(out, "skDER_Results.txt")
     if p.returncode != 0 or not os.path.exists(res):
         raise RuntimeError("reference skder failed (rc %d):\n%s" % (p.returncode, p.stdout[-4000:]))
@@ -63,25 +64,21 @@ def run_skder(genome_dir_or_files, outdir, mode="greedy", ani=99.0, af=50.0, thr
     return wall, reps, out
 
 
-def phases_from_log(outdir):
-    """Wall seconds between the reference's own Progress.log entries: {label: seconds}."""
-    import datetime as dt
-    import re
-
-    path = os.path.join(outdir, "Progress.log")
-    rows = []
-    for ln in open(path, errors="replace"):
-        m = re.match(r"(\d{4}-\d\d-\d\d \d\d:\d\d:\d\d),(\d+) - (.*)", ln)
-        if m:
-            t = dt.datetime.strptime(m.group(1), "%Y-%m-%d %H:%M:%S").timestamp() + int(m.group(2)) / 1e3
-            rows.append((t, m.group(3)))
-    ph = {}
-    for (t0, a), (t1, b) in zip(rows[:-1], rows[1:]):
-        if a.startswith("Running "):
-            key = a.split()[1] + (" " + a.split()[2] if a.split()[1] == "skani" else "")
-            ph[key] = ph.get(key, 0.0) + (t1 - t0)
-    if rows:
-        ph["total_logged"] = rows[-1][0] - rows[0][0]
+def phases_from_files(outdir, t_start, t_end):
+    """Wall seconds of the reference's stages, from the modification times of the files each stage leaves behind (its
+    own Progress.log has minute resolution): {stage: seconds}.  t_start / t_end: time.time() around the run."""
+    marks = [("list_genomes", "All_Genomes_Listing.txt"), ("n50", "Concatenated_N50.txt"),
+             ("skani_triangle", "Skani_Triangle_Edge_Output.txt"),
+             ("skDERsum", "Genome_Information_for_Greedy_Clustering.txt"),
+             ("sort", "Genome_Information_for_Greedy_Clustering.sorted.txt"), ("select_representatives", "skDER_Results.txt")]
+    ph, last = {}, t_start
+    for name, f in marks:
+        p = os.path.join(outdir, f)
+        if os.path.exists(p):
+            t = os.stat(p).st_mtime
+            ph[name] = max(0.0, t - last)
+            last = max(last, t)
+    ph["copy_representatives_and_exit"] = max(0.0, t_end - last)
     return ph
 
 
@@ -98,4 +95,4 @@ if __name__ == "__main__":
     a = ap.parse_args()
     w, reps, out = run_skder(a.genomes, a.outdir, a.mode, a.ani, a.af, clusters=a.n)
     print("%.2f s, %d representatives" % (w, len(reps)))
-    print(phases_from_log(out))
+    print(run_skder.last_phases)
