@@ -176,6 +176,12 @@ int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_see
  * owned_only).  Every rank therefore probes only tables it built itself, and a reference's pairs stay together on one
  * GPU (L2 reuse), however the survivors are distributed over the rows. */
 int skb_set_owned(skb_ctx *ctx, int32_t first, int32_t count); /* count = -1: all genomes (the default) */
+/* A rank builds the seed tables and repeat flags of its OWN genomes before the exchange (skb_index_seed_tables: the first
+ * half of skb_index), keeps them across the reset (skb_clear_keep_tables instead of skb_clear), imports everybody's
+ * sketches with their repeat flags, declares the same genomes owned, and calls skb_index: the tables are reused, only the
+ * chunk tables and the marker index of the whole set are built.  Table work and memory per rank: 1/P, done once. */
+int skb_index_seed_tables(skb_ctx *ctx);
+int skb_clear_keep_tables(skb_ctx *ctx);
 int skb_screen_triangle(skb_ctx *ctx, double screen_pct, int32_t part, int32_t n_parts, const uint64_t **dev_pairs,
                         int64_t *n_pairs, skb_stats *stats);
 /* dev_pairs: (a << 32 | b) on this device; edges may be NULL (result stays on the device, skb_device_edges) */

@@ -281,40 +281,50 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                 }
             };
             relax(me + 1);  // d = 0, the nearest predecessor: ties keep it
-            // Short cut.  Colinear anchors (the usual case) chain onto the nearest predecessor with a score no other
-            // one can reach; then the other 15 are not looked at.  Mx bounds what they can offer: the largest F among
-            // the earlier anchors whose diagonal lies within max_gap + DIAG_SLACK of Dref, where Dref follows this
-            // task's current diagonal to within DIAG_SLACK.  An anchor further off than that is out of max_gap for
-            // this one, and one inside offers F - gap <= Mx: if Mx <= best nothing replaces `best` (a later
-            // predecessor only wins with a strictly larger candidate) -- the same result as the full scan.  When the
-            // diagonal jumps (contig end, indel, rearrangement) Mx is rebuilt for the new diagonal from the window, so
-            // the old chain's high scores do not keep the short cut off for the next 16 anchors.  Stale entries that
-            // have left the window only make Mx too large (a missed short cut).
+            relax(me + 2);  // d = 1
+            // Short cut.  Colinear anchors (the usual case) chain onto one of the two nearest predecessors with a score
+            // no other one can reach; then the other 14 are not looked at.  (Two, because a chance anchor -- FracMinHash
+            // samples the same 1/125 of k-mer space in both genomes, so ~1.7 % of a pair's anchors are random matches
+            // on a random diagonal -- sits between two anchors of a chain, and the one after it must reach over it.)
+            // Mx bounds what predecessors beyond the nearest two can offer: the largest F among those whose diagonal
+            // lies within max_gap + DIAG_SLACK of Dref, where Dref follows this task's current diagonal to within
+            // DIAG_SLACK.  An anchor further off than that is out of max_gap for this one, and one inside offers
+            // F - gap <= Mx: if Mx <= best nothing replaces `best` (a later predecessor only wins with a strictly
+            // larger candidate) -- the same result as the full scan.  An anchor off the current diagonal gets its own
+            // bound (m2) from the window; the diagonal is adopted as the new Dref only when the previous anchor lies
+            // on it too (contig end, indel, rearrangement -- not a chance anchor), so the old chain's high scores
+            // neither keep the short cut off for the next 16 anchors nor does one stray anchor derail it.  Stale
+            // entries that have left the window only make Mx too large (a missed short cut).
             long long dj = (long long)Di - Dref;  // 64-bit: opposite strands are up to 2^32 apart
             dj = dj < 0 ? -dj : dj;
             const bool jump = live && dj > DIAG_SLACK;
+            bool settled = !live || Mx <= best;
             if (__any_sync(0xffffffffu, jump)) {
                 int m2 = NEG_F;
 #pragma unroll
-                for (int d = 1; d < LB; d++) {
+                for (int d = 2; d < LB; d++) {
                     int dd = D[me + 1 + d] - Di;
                     dd = dd < 0 ? -dd : dd;
                     m2 = max(m2, dd <= diag_lim ? F[me + 1 + d] : NEG_F);
                 }
                 if (jump) {
-                    Mx = m2;
-                    Dref = Di;
+                    settled = m2 <= best;
+                    long long dp = (long long)Di - D[me + 1];
+                    dp = dp < 0 ? -dp : dp;
+                    if (dp <= DIAG_SLACK) {  // the previous anchor is on this diagonal too: follow it
+                        Mx = m2;
+                        Dref = Di;
+                    }
                 }
             }
-            const bool settled = !live || Mx <= best;
             if (!__all_sync(0xffffffffu, settled)) {
 #pragma unroll
-                for (int d = 1; d < LB; d++) relax(me + 1 + d);
+                for (int d = 2; d < LB; d++) relax(me + 1 + d);
             }
-            {  // the nearest predecessor is an "other" one for the next anchor
-                int dd = D[me + 1] - Dref;
+            {  // the second nearest predecessor is beyond the nearest two of the next anchor
+                int dd = D[me + 2] - Dref;
                 dd = dd < 0 ? -dd : dd;
-                Mx = max(Mx, dd <= diag_lim ? F[me + 1] : NEG_F);
+                Mx = max(Mx, dd <= diag_lim ? F[me + 2] : NEG_F);
             }
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;

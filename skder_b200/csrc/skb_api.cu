@@ -115,6 +115,11 @@ struct skb_ctx {
     bool indexed = false;
     int32_t n_indexed = 0;
     int32_t own_first = 0, own_count = -1;  // genomes whose seed tables this context builds (skb_set_owned); -1: all
+    // seed tables built by skb_index_seed_tables and carried across skb_clear_keep_tables: valid for a context that owns
+    // exactly these genomes (count, seed records, table density)
+    int32_t kept_n = 0;
+    uint64_t kept_seeds = 0;
+    int kept_x2 = 0;
     int tab_x2 = 4;        // seed-table buckets per seed, times two: 4 / 2 / 1 = 0.5 / 1 / 2 records per 4-slot bucket
     int tab_x2_forced = 0; // SKB_TAB_X2 (tests exercise the overflow chain with 1)
     DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
@@ -742,6 +747,7 @@ int skb_clear(skb_ctx *ctx) {
         ctx->add_calls.clear();
         ctx->own_first = 0;
         ctx->own_count = -1;
+        ctx->kept_n = 0;
         ctx->h_tab_off.assign(1, 0);
         ctx->h_tab_buckets.clear();
         ctx->h_ctg_pstart.clear();
@@ -864,19 +870,25 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
     });
 }
 
-int skb_index(skb_ctx *ctx) {
-    return guarded(ctx, [&]() -> int {
-        skb_ctx *c = ctx;
+static int index_impl(skb_ctx *c, bool tables_only) {
+    {
         const int32_t n = c->n();
         if (n == 0) return fail(c, SKB_ESTATE, "no genomes added");
         const uint64_t n_seeds = c->h_seed_off.back();
+        (void)n_seeds;
+        uint64_t own_seeds_now = 0;
+        for (int32_t g = 0; g < n; g++)
+            if (c->owns(g)) own_seeds_now += c->h_seed_off[g + 1] - c->h_seed_off[g];
+        const int32_t own_n_now = c->own_count < 0 ? n : std::max(0, std::min(c->own_first + c->own_count, n) - std::min(c->own_first, n));
+        // tables of exactly the owned genomes are already in d_tab (built before the sketches were exchanged)
+        const bool reuse = !tables_only && c->kept_n > 0 && c->kept_n == own_n_now && c->kept_seeds == own_seeds_now;
         // ---- host-side tables: seed hash sizes, contigs in padded coordinates, chunks
         std::vector<uint64_t> &tab_off = c->h_tab_off;
         std::vector<uint32_t> &tab_buckets = c->h_tab_buckets, &ctg_pstart = c->h_ctg_pstart, &chunk_start = c->h_chunk_start,
                               &chunk_len = c->h_chunk_len;
         // the sparsest seed tables the device holds comfortably: a lookup is one sector read unless its bucket
         // overflowed, and at 0.5 records per bucket that is rare enough not to stall a warp (skb_probe.cuh)
-        c->tab_x2 = c->tab_x2_forced;
+        c->tab_x2 = reuse ? c->kept_x2 : c->tab_x2_forced;
         if (!c->tab_x2) {
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -927,9 +939,10 @@ int skb_index(skb_ctx *ctx) {
         c->d_chunk_len.upload(chunk_len, c->st);
         c->d_chunk_off.upload(c->h_chunk_off, c->st);
         // ---- K2: seed hash indices + repeat flags + chunk_begin
-        c->d_tab.reserve(tab_off[n] + BUCKET, 0, c->st);
-        CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
-        {   // the owned genomes are one contiguous id range, so their seeds are one contiguous range too; the repeat
+        c->d_tab.reserve(tab_off[n] + BUCKET, reuse ? tab_off[n] : 0, c->st);
+        if (!reuse) {
+            CK(cudaMemsetAsync(c->d_tab.p, 0xFF, tab_off[n] * 8, c->st));
+            // the owned genomes are one contiguous id range, so their seeds are one contiguous range too; the repeat
             // flags of the others arrived with their seeds (skb_import_sketches keeps them)
             const int32_t o0 = c->own_count < 0 ? 0 : std::min(c->own_first, n);
             const int32_t o1 = c->own_count < 0 ? n : std::min(c->own_first + c->own_count, n);
@@ -943,6 +956,15 @@ int skb_index(skb_ctx *ctx) {
                 CK(cudaGetLastError());
                 c->launches += 3;
             }
+        }
+        c->kept_n = 0;
+        if (tables_only) {  // the caller exchanges sketches next (skb_clear_keep_tables): nothing else is needed yet
+            CK(cudaStreamSynchronize(c->st));
+            c->kept_n = own_n_now;
+            c->kept_seeds = own_seeds_now;
+            c->kept_x2 = c->tab_x2;
+            c->indexed = false;
+            return SKB_OK;
         }
         const uint32_t n_entries = (uint32_t)chunk_start.size() + (uint32_t)n;
         c->d_chunk_begin.reserve(n_entries, 0, c->st);
@@ -996,7 +1018,32 @@ int skb_index(skb_ctx *ctx) {
         c->n_mkeys_indexed = c->n_mkeys;
         c->indexed = true;
         return SKB_OK;
-    });
+    }
+}
+
+int skb_index(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int { return index_impl(ctx, false); });
+}
+
+// Seed tables and repeat flags of the genomes added so far, nothing else: the first half of skb_index, for a rank that is
+// about to exchange sketches.  With skb_clear_keep_tables the tables survive the exchange, and the skb_index that follows
+// (after skb_import_sketches + skb_set_owned for the same genomes) reuses them instead of building them again.
+int skb_index_seed_tables(skb_ctx *ctx) {
+    return guarded(ctx, [&]() -> int { return index_impl(ctx, true); });
+}
+
+int skb_clear_keep_tables(skb_ctx *ctx) {
+    if (!ctx) return SKB_EINVAL;
+    const int32_t kn = ctx->kept_n;
+    const uint64_t ks = ctx->kept_seeds;
+    const int kx = ctx->kept_x2;
+    const int rc = skb_clear(ctx);
+    if (rc == SKB_OK) {
+        ctx->kept_n = kn;
+        ctx->kept_seeds = ks;
+        ctx->kept_x2 = kx;
+    }
+    return rc;
 }
 
 // Index the genomes added since the last skb_index / skb_index_append as QUERY-ONLY additions: their

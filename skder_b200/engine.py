@@ -133,8 +133,14 @@ class Engine:
         self.add(packed)
         return packed
 
-    def clear(self):
-        self._ck(self._L.skb_clear(self._h), "skb_clear")
+    def clear(self, keep_tables=False):
+        if keep_tables:
+            self._ck(self._L.skb_clear_keep_tables(self._h), "skb_clear_keep_tables")
+        else:
+            self._ck(self._L.skb_clear(self._h), "skb_clear")
+
+    def index_seed_tables(self):
+        self._ck(self._L.skb_index_seed_tables(self._h), "skb_index_seed_tables")
 
     def timer_start(self):
         self._ck(self._L.skb_timer_start(self._h), "skb_timer_start")

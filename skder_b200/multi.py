@@ -29,13 +29,27 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
     """Every rank holds the sketches of its own genomes; afterwards every rank holds all of them,
     ordered by (rank, local order).  Collective: all ranks must call.
 
-    sharded_index: the rank first indexes its own genomes (their repeat flags are part of the seed records and travel
-    with them) and afterwards owns exactly those genomes (skb_set_owned): the next Engine.index() builds seed tables
-    for them only -- 1/P of the table work and memory per rank -- and triangle_sharded() sends every pair to the rank
-    that owns its reference genome."""
+    sharded_index: the rank first builds the seed tables of its own genomes (their repeat flags are part of the seed
+    records and travel with them), keeps the tables across the exchange, and afterwards owns exactly those genomes
+    (skb_set_owned): the next Engine.index() reuses the tables and adds only the chunk tables and the marker index of
+    the whole set -- 1/P of the table work and memory per rank, done once -- and triangle_sharded() sends every pair to
+    the rank that owns its reference genome."""
+    import os
+    import sys
+    import time
+
+    prof = os.environ.get("SKB_REPL_PROFILE") == "1"
+    tm = [time.perf_counter()]
+
+    def lap():
+        if prof:
+            torch.cuda.synchronize()
+            tm.append(time.perf_counter())
+
     world, rank = dist.get_world_size(), dist.get_rank()
     if sharded_index and eng.n_genomes:
-        eng.index()
+        eng.index_seed_tables()
+    lap()
     device = torch.device("cuda", eng.device)
     v = eng.sketch_view()
     n = v.n_genomes
@@ -47,6 +61,7 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
         "ctg_len": np.ctypeslib.as_array(v.host_ctg_len, shape=(max(int(v.n_contigs), 1),))[: int(v.n_contigs)].copy(),
     }
     metas = _exchange_meta(meta, dist, torch, torch.device("cuda", eng.device) if dist.get_backend() == "nccl" else None)
+    lap()
     gathered = []
     for key, ptr, cnt in (("n_seeds", v.dev_seeds, v.n_seeds), ("n_mkeys", v.dev_marker_keys, v.n_marker_keys)):
         mx = max(int(m[key]) for m in metas)
@@ -57,7 +72,8 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
         dist.all_gather_into_tensor(recv, send)
         gathered.append((recv, max(mx, 1)))
     torch.cuda.synchronize(device)
-    eng.clear()
+    lap()
+    eng.clear(keep_tables=sharded_index)
     (seeds, s_stride), (mkeys, m_stride) = gathered
     for r, m in enumerate(metas):
         if m["n"] == 0:
@@ -75,6 +91,10 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
         )
     if sharded_index:
         eng.set_owned(sum(int(m["n"]) for m in metas[:rank]), int(metas[rank]["n"]))
+    lap()
+    if prof and rank == 0:
+        sys.stderr.write("replicate: own index %.2f  meta %.2f  all-gather %.2f  import %.2f ms\n" % tuple(
+            (b - a) * 1e3 for a, b in zip(tm, tm[1:])))
     return metas
 
 
