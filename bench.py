@@ -44,6 +44,7 @@ SKDER_ANI, SKDER_AF = 99.5, 50.0           # skDER's default cutoffs (bin/skder:
 # bounded sample the `cpu_baseline` leg of OUR arm is timed on (same generator): 80 clades x 5 members keeps the
 # workload's survivor fraction (1.0 % vs 0.98 %)
 CPU_SAMPLE_CLADES, CPU_SAMPLE_PER_CLADE = 80, 5
+SEARCH_WORKLOADS = ("config4", "tiny4")  # low_mem_greedy: the `skani sketch` + `skani search` path
 REF_BUDGET_S = float(os.environ.get("SKB_REF_BUDGET_S", "240"))  # wall budget of the reference arm's timed steps
 
 
@@ -61,7 +62,7 @@ def workload_shape(name):
 def workload_name(w):
     nc, per, L, Lhi, *_ = cfg(w)
     size = "%.1f Mbp" % (L / 1e6) if Lhi is None else "%.0f-%.0f Mbp" % (L / 1e6, Lhi / 1e6)
-    if w == "config4":
+    if w in SEARCH_WORKLOADS:
         return ("%s: %d synthetic %s genomes (%d clades x %d), low_mem_greedy: `skani sketch` once, then the greedy loop of "
                 "`skani search` calls (skani defaults -s 80 --min-af 15), skDER cutoffs 99.5 / 50" % (w, nc * per, size, nc, per))
     return ("%s: %d synthetic %s genomes (%d clades x %d, 95-99.9%% ANI within clade), skDER default thresholds: greedy and "
@@ -189,7 +190,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     nc, per, L = workload_shape(args.workload)
     n_full = nc * per
-    if args.workload == "config4":
+    if args.workload in SEARCH_WORKLOADS:
         return run_reference_search(args, threads)
     pairs_full = n_full * (n_full - 1) // 2
     surv_full = nc * per * (per - 1) // 2
@@ -413,7 +414,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if args.workload == "config4":
+    if args.workload in SEARCH_WORKLOADS:
         return run_ours_search(args, torch, dist, rank, world, local)
 
     nc, per, L = workload_shape(args.workload)
@@ -621,39 +622,86 @@ def run_ours(args):
 
 def run_ours_search(args, torch, dist, rank, world, local):
     """config4: `skder -d low_mem_greedy` (reference src/skDER/skder.py:95-134) -- sketch the database once, then the
-    greedy loop: in N50 order, every genome not yet accounted for is searched against the database.  The database is
-    sharded over the ranks (N/P genomes each, no replication); every rank sketches the query itself (that is cheaper
-    than shipping its sketch) and searches its shard; the hits' genome numbers are all-gathered into the accounted set."""
+    greedy loop: in N50 order, every genome not yet accounted for is searched against the database.  SURVEY 8e: the
+    database is sharded over the ranks (N/P genomes each, no replication); the rank that holds the query sketches it
+    and broadcasts the sketch (seed records + marker keys, ~0.2 MB); every rank searches its shard; the hits' genome
+    numbers are all-gathered into the accounted set.  The loop is sequential by construction."""
     from concurrent.futures import ThreadPoolExecutor
 
-    from skder_b200 import _lib, engine, synth
+    from skder_b200 import _lib, engine, multi, synth
 
     nc, per, L = workload_shape(args.workload)
+    nc = int(os.environ.get("SKB_SEARCH_CLADES", nc))  # bounded runs of the same shape
     n_full = nc * per
     t_gen = time.perf_counter()
+    my_clades = list(range(rank, nc, world))
 
     def gen(c):
         return [engine.pack_contigs(g) for g in synth.clade_of(args.workload, c)]
 
     with ThreadPoolExecutor(max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))) as ex:
-        clades = list(ex.map(gen, range(nc)))  # every rank needs every genome as a potential query
+        clades = list(ex.map(gen, my_clades))
     packed = [g for cl in clades for g in cl]
+    my_ids = np.array([c * per + m for c in my_clades for m in range(per)], np.int64)  # workload-wide genome numbers
+    local_of = {int(g): i for i, g in enumerate(my_ids)}
     t_gen = time.perf_counter() - t_gen
-    n50 = np.array([p.n50 for p in packed])
+    n50 = np.zeros(n_full, np.int64)
+    n50[my_ids] = [p.n50 for p in packed]
+    if world > 1:
+        t = torch.from_numpy(n50).cuda()
+        dist.all_reduce(t)
+        n50 = t.cpu().numpy()
     order = sorted(range(n_full), key=lambda g: (-int(n50[g]), g))
-    mine = [g for g in range(n_full) if (g // per) % world == rank]  # database shard: whole clades, dealt round-robin
-    my_ids = np.array(mine, np.int64)
-    pin, views, keep, h2d_bytes = pinned_views([packed[g] for g in mine], torch)
+    pin, views, keep, h2d_bytes = pinned_views(packed, torch)
     arr = (C.POINTER(_lib.Packed) * len(views))(*[C.pointer(v) for v in views])
     eng = engine.Engine(local)
+    dev = torch.device("cuda", local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def add_query(g):
+        """the query becomes genome n_db of every rank's context: sketched by its owner, imported by the others"""
+        owner = (g // per) % world
+        n_db = eng.n_genomes
+        if world == 1:
+            eng.add([packed[local_of[g]]])
+            return
+        head = torch.zeros(4, dtype=torch.int64, device=dev)
+        if rank == owner:
+            eng.add([packed[local_of[g]]])
+            v = eng.sketch_view()
+            so = np.ctypeslib.as_array(v.host_seed_off, shape=(n_db + 2,))
+            co = np.ctypeslib.as_array(v.host_ctg_off, shape=(n_db + 2,))
+            s0, ns = int(so[n_db]), int(so[n_db + 1] - so[n_db])
+            nctg = int(co[n_db + 1] - co[n_db])
+            mk0 = add_query.mk_before
+            nm = int(v.n_marker_keys) - mk0
+            tl = int(np.ctypeslib.as_array(v.host_total_len, shape=(n_db + 1,))[n_db])
+            head = torch.tensor([ns, nm, nctg, tl], dtype=torch.int64, device=dev)
+        dist.broadcast(head, src=owner)
+        ns, nm, nctg, tl = (int(x) for x in head.tolist())
+        buf = torch.empty(ns + nm + nctg, dtype=torch.int64, device=dev)
+        if rank == owner:
+            buf[:ns].copy_(multi._dev_tensor(torch, v.dev_seeds + 8 * s0, ns, dev))
+            # marker keys carry the sender's genome number in their low 22 bits: rebase to 0 for the receivers
+            buf[ns:ns + nm].copy_(multi._dev_tensor(torch, v.dev_marker_keys + 8 * mk0, nm, dev) - n_db)
+            cl = np.ctypeslib.as_array(v.host_ctg_len, shape=(int(v.n_contigs),))[int(co[n_db]):int(co[n_db + 1])]
+            buf[ns + nm:].copy_(torch.from_numpy(cl.astype(np.int64)))
+        dist.broadcast(buf, src=owner)
+        if rank != owner:
+            torch.cuda.current_stream(dev).synchronize()
+            cl = buf[ns + nm:].cpu().numpy().astype(np.uint32)
+            so = np.array([0, ns], np.uint64)
+            tls = np.array([tl], np.uint64)
+            co = np.array([0, nctg], np.uint32)
+            eng._ck(eng._L.skb_import_sketches(eng._h, 1, C.c_void_p(buf.data_ptr()), ns, C.c_void_p(buf.data_ptr() + 8 * ns), nm,
+                                               so.ctypes.data, tls.ctypes.data, co.ctypes.data, cl.ctypes.data, 0), "skb_import_sketches")
+
     def one_run():
-        """sketch + index the shard, then the greedy loop; returns (reps, searches, pairs, t_sketch, t_loop, launches)"""
+        """sketch + index the shard, then the greedy loop; returns (reps, pairs, t_sketch, t_loop, launches)"""
         l0 = eng.launches
         t0 = time.perf_counter()
         eng.clear()
@@ -661,32 +709,40 @@ def run_ours_search(args, torch, dist, rank, world, local):
         eng.index()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        n_db = eng.n_genomes
+        add_query.mk_before = int(eng.sketch_view().n_marker_keys)
+        all_db = np.arange(n_db, dtype=np.int32)
         accounted = np.zeros(n_full, bool)
         reps = 0
         for g in order:
             if accounted[g]:
                 continue
             reps += 1
-            edges, st = eng.search(packed[g], screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
+            add_query(g)
+            try:
+                eng.index_append()
+                edges, st = eng.rect(all_db, [n_db], screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
+            finally:
+                eng.pop_last_add()
             # skder.py:128: ANI >= cutoff and the AF in column 4 (the query's) >= cutoff, on the printed 2-decimal values
             hit = (np.round(edges["ani"], 2) >= SKDER_ANI) & (np.round(edges["af_b"], 2) >= SKDER_AF)
             ids = my_ids[edges["a"][hit]]
             if world > 1:
-                cnt = torch.tensor([len(ids)], device="cuda", dtype=torch.int64)
-                cnts = torch.zeros(world, device="cuda", dtype=torch.int64)
+                cnt = torch.tensor([len(ids)], device=dev, dtype=torch.int64)
+                cnts = torch.zeros(world, device=dev, dtype=torch.int64)
                 dist.all_gather_into_tensor(cnts, cnt)
-                mx = int(cnts.max())
-                send = torch.full((max(mx, 1),), -1, device="cuda", dtype=torch.int64)
+                mx = max(int(cnts.max()), 1)
+                send = torch.full((mx,), -1, device=dev, dtype=torch.int64)
                 if len(ids):
-                    send[: len(ids)] = torch.from_numpy(ids).cuda()
-                recv = torch.empty(world * max(mx, 1), device="cuda", dtype=torch.int64)
+                    send[: len(ids)] = torch.from_numpy(ids).to(dev)
+                recv = torch.empty(world * mx, device=dev, dtype=torch.int64)
                 dist.all_gather_into_tensor(recv, send)
                 ids = recv[recv >= 0].cpu().numpy()
             accounted[ids] = True
             accounted[g] = True
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        return reps, reps, reps * n_full, t1 - t0, t2 - t1, eng.launches - l0
+        return reps, reps * n_full, t1 - t0, t2 - t1, eng.launches - l0
 
     for _ in range(min(args.warmup, 1)):
         one_run()
@@ -699,27 +755,35 @@ def run_ours_search(args, torch, dist, rank, world, local):
         barrier()
         t_all = time.perf_counter() - t0
     if world > 1:
-        tt = torch.tensor([t_all], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([t_all, float(np.mean([r[3] for r in res]))], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_all = float(tt[0])
+        t_all, t_loop = float(tt[0]), float(tt[1])
+        ll = torch.tensor([res[-1][4]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ll)
+        launches_all = int(ll[0])
+    else:
+        t_loop, launches_all = float(np.mean([r[3] for r in res])), res[-1][4]
     if rank == 0:
-        reps, searches, pairs, t_sk, t_loop, launches = res[-1]
+        reps, pairs, t_sk, _, launches = res[-1]
         t_step = t_all / args.steps
         line = {
-            "metric": "genome pairs/sec ANI+AF (search path)", "value": pairs / float(np.mean([r[4] for r in res])), "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": float(np.mean([r[4] for r in res])) * 1e3,
+            "metric": "genome pairs/sec ANI+AF (search path)", "value": pairs / t_loop, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t_loop * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/int32 + f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "representatives": reps, "searches": searches,
-                       "pairs": pairs, "searches_per_s": searches / float(np.mean([r[4] for r in res])),
-                       "ms_sketch_index_db": float(np.mean([r[3] for r in res])) * 1e3, "gen_s": t_gen,
-                       "timing": "host clock between device synchronisations (the loop is sequential host logic around "
-                                 "~%d small launches per search)" % max(1, launches // max(searches, 1)),
-                       "sharding": "database sharded N/P per rank, query sketched on every rank, hit ids all-gathered"},
+            "config": {"workload": workload_name(args.workload) if nc == workload_shape(args.workload)[0] else
+                       "%s, first %d clades only (%d genomes)" % (workload_name(args.workload), nc, n_full),
+                       "representatives": reps, "searches": reps, "pairs": pairs, "searches_per_s": reps / t_loop,
+                       "ms_per_search": t_loop / reps * 1e3, "ms_sketch_index_db": float(np.mean([r[2] for r in res])) * 1e3,
+                       "gen_s": t_gen,
+                       "timing": "host clock between device synchronisations, max over ranks: the loop is sequential host "
+                                 "logic around ~%d small launches per search" % max(1, launches // max(reps, 1)),
+                       "sharding": "database sharded N/P per rank; the query is sketched by the rank that holds it and its "
+                                   "sketch broadcast; hit ids all-gathered" if world > 1 else "one GPU holds the database"},
             "clocks": clk.summary(),
-            "e2e": {"value": pairs / t_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes * world + sum(
-                packed[g].n_words * 8 for g in order[:1]) * searches), "d2h_bytes_per_step": int(32 * per * searches),
-                    "ms_per_step": t_step * 1e3},
-            "gpu_launches": int(launches * args.steps),
+            "e2e": {"value": pairs / t_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes) * world + reps * int(L // 4),
+                    "d2h_bytes_per_step": int(32 * per * reps), "ms_per_step": t_step * 1e3,
+                    "note": "database upload + sketch + index + the whole search loop (queries uploaded one by one)"},
+            "gpu_launches": int(launches_all * args.steps),
         }
         print(json.dumps(line))
     if world > 1:
@@ -733,7 +797,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", default="config3", choices=["tiny", "tinyr", "config2", "config3", "config3r", "config4", "config5"])
+    ap.add_argument("--workload", default="config3", choices=["tiny", "tinyr", "tiny4", "config2", "config3", "config3r", "config4", "config5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample")
     ap.add_argument("--derep", choices=["off", "sample", "full"], default=os.environ.get("SKB_BENCH_DEREP", "full"),

@@ -1745,6 +1745,7 @@ int skb_import_sketches(skb_ctx *ctx, int32_t n_genomes, const uint64_t *dev_see
         if (n_genomes == 0) return SKB_OK;
         if ((uint64_t)c->n() + (uint64_t)n_genomes >= GID_MASK) return fail(c, SKB_ELIMIT, "too many genomes");
         const uint64_t cur = c->h_seed_off.back();
+        c->add_calls.push_back({c->n(), c->n_mkeys});  // skb_pop_last_add undoes an import like an add
         c->d_seeds.reserve(cur + (uint64_t)n_seeds + 1, cur, c->st);
         c->d_mkeys.reserve(c->n_mkeys + (uint64_t)n_marker_keys + 1, c->n_mkeys, c->st);
         if (n_seeds && keep_repeat_flags)  // the sender indexed its genomes: their repeat flags travel with the seeds

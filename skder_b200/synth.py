@@ -108,6 +108,7 @@ CONFIGS = {
     # of the probe (multi-hit seeds, repeat flags) and of the chaining DP (non-zero gaps) are on the timed path
     "config3r": (100, 50, 5_000_000, None, 0.0005, 0.025, 20261017 + 33),
     "tinyr": (3, 4, 200_000, None, 0.0005, 0.025, 20261017 + 34),
+    "tiny4": (4, 6, 150_000, None, 0.0002, 0.004, 20261017 + 35),  # config4's shape in small: close relatives, search path
     "config4": (200, 100, 2_800_000, None, 0.0005, 0.01, 20261017 + 4),
     "config5": (500, 100, 2_000_000, 8_000_000, 0.0005, 0.025, 20261017 + 5),
 }

@@ -583,3 +583,34 @@ def test_reference_sharded_triangle_single_process(eng7, ora7, oracle, genomes7,
             assert np.array_equal(cat, np.sort(full, order=["a", "b"]))
         else:  # genome 2 is owned by nobody: exactly the pairs with reference 2 are missing
             assert len(cat) < len(full) and set(map(tuple, cat[["a", "b"]].tolist())) < set(map(tuple, full[["a", "b"]].tolist()))
+
+
+def _bench_line(argv, nproc=1, timeout=900):
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py")] + argv
+    if nproc > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
+               "--master-port", str(29900 + os.getpid() % 90), os.path.join(root, "bench.py")] + argv
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert out.returncode == 0 and lines, out.stdout[-1500:] + out.stderr[-3000:]
+    return json.loads(lines[-1])
+
+
+def test_search_loop_selects_what_the_oracle_loop_selects(built_lib, oracle):
+    """bench.py's config4 path (the low_mem_greedy loop of reference skder.py:116-133 on a resident database) on a small
+    set of the same shape: as many representatives as the same loop over the oracle's `search`."""
+    sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+
+    sys.path.insert(0, sys_path)
+    import bench
+
+    want = bench.cpu_search_loop("tiny4", 4, 4, 6)
+    got = _bench_line(["--workload", "tiny4", "--steps", "1", "--warmup", "0"])
+    assert got["config"]["representatives"] == want["reps"] and got["config"]["pairs"] == want["reps"] * want["n"]
+    assert got["gpu_launches"] > 0

@@ -58,3 +58,30 @@ def test_two_gpu_sharded_triangle_equals_single_gpu(built_lib, tmp_path):
 
     r = json.loads(line[0][7:])
     assert r["equal"] and r["n"] == r["n_want"] == 18, r
+
+
+def test_two_gpu_search_loop_equals_single_gpu(built_lib):
+    """config4's multi-GPU design (database sharded per rank, query sketch broadcast, hit ids all-gathered) selects the
+    same number of representatives as one GPU holding the whole database."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_gpu_parity import _bench_line
+
+    one = _bench_line(["--workload", "tiny4", "--steps", "1", "--warmup", "0"])
+    two = _bench_line(["--workload", "tiny4", "--gpus", "2", "--steps", "1", "--warmup", "0"], nproc=2)
+    assert two["n_gpus"] == 2 and two["config"]["representatives"] == one["config"]["representatives"]
+
+
+def test_two_gpu_bench_checksum_equals_single_gpu(built_lib):
+    """bench.py's edge checksum: N = 2 (reference-sharded) and N = 1 produce the same canonical edge list."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_gpu_parity import _bench_line
+
+    a = _bench_line(["--workload", "tinyr", "--steps", "1", "--warmup", "1", "--no-cpu", "--no-parity", "--derep", "off"])
+    b = _bench_line(["--workload", "tinyr", "--gpus", "2", "--steps", "1", "--warmup", "1", "--no-cpu", "--no-parity", "--derep", "off"], nproc=2)
+    assert a["edges_sha256"] == b["edges_sha256"] and a["config"]["edges"] == b["config"]["edges"] > 0
