@@ -115,7 +115,8 @@ static_assert(sizeof(TaskDesc) == 32, "desc size");
 
 // task_off: GLOBAL exclusive scan of the chunk counts, pointing at this batch's first pair; base = its value there
 __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-                                  uint32_t base, int64_t n_pairs, uint32_t n_tasks, TaskDesc *__restrict__ desc) {
+                                  uint32_t base, int64_t n_pairs, uint32_t n_tasks, TaskDesc *__restrict__ desc,
+                                  uint32_t *__restrict__ task_pair) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tasks) return;
     int64_t lo = 0, hi = n_pairs - 1;
@@ -138,6 +139,7 @@ __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, 
     d.tab_idx = db.g_tab_off[pi.r];
     d.nb = db.g_tab_buckets[pi.r];
     desc[t] = d;
+    task_pair[t] = (uint32_t)lo;
 }
 
 // ---- K4a: anchors.  One warp per task; the only dependent reads are descriptor -> seed records ->
@@ -184,15 +186,32 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
     }
 }
 
-// ---- K4b: chaining DP, one THREAD per task.  The look-back window lives in registers and ROTATES:
-//   A[UNR + d] = d-th previous anchor (d = 0 nearest); the UNR anchors of one iteration sit in
-//   A[UNR-1 .. 0]; after the iteration everything shifts by UNR.  (A 16x unrolled static window needs
-//   no moves but is ~50 KB of code: ncu showed 64% of stalls on instruction fetch.)
+// ---- K4b: chaining DP, one THREAD per task.
 //   Q = q_rel + (rev << 20) + 1: other strand relation => more than band apart, no extra test;
 //       the +1 makes (Qi - Q[j]) == dq - 1, so one unsigned compare checks 0 < dq <= band
 //   D = R - q with R = rev ? -ref_pos : ref_pos: gap = |D_i - D_j|, d_ref = (D_i - D_j) + dq
-//   F = f + anchor_score
-__global__ void __launch_bounds__(DP_THREADS, 4)
+//   F = f + anchor_score (0 = empty slot: it can never beat `best`, which starts at anchor_score)
+// Colinear anchors (the usual case) chain onto one of the two nearest predecessors with a score no other one can
+// reach.  So only those two live in registers; the full 16-deep look-back window is a ring in shared memory
+// ([slot][thread]: conflict-free, slot = anchor index & 15), written once per anchor and read only on the two rare
+// paths: the full scan (the short cut could not prove the nearest two sufficient) and the bound rebuild.
+//
+// Short cut.  Mx bounds what predecessors beyond the nearest two can offer: the largest F among those whose diagonal
+// lies within max_gap + DIAG_SLACK of Dref, where Dref follows this task's current diagonal to within DIAG_SLACK.
+// An anchor further off than that is out of max_gap for this one, and one inside offers F - gap <= Mx: if
+// Mx <= best nothing replaces `best` (a later predecessor only wins with a strictly larger candidate) -- the same
+// result as the full scan.  (Two nearest, not one: FracMinHash samples the same 1/125 of k-mer space in both
+// genomes, so ~1.7 % of a pair's anchors are chance matches on a random diagonal; one sits between two anchors of a
+// chain and the one after it must reach over it.)  An anchor off the current diagonal (`jump`) needs its own bound
+// m2 = max F over the window within reach of ITS diagonal.  `off` keeps one bit per window entry: set iff that
+// anchor was off Dref's diagonal when it entered.  If no entry beyond the nearest two is off and the anchor is more
+// than max_gap + 2 DIAG_SLACK from Dref, every such entry is out of its reach: m2 is empty without looking (chance
+// anchors, and the first anchor after a contig end or rearrangement).  Otherwise the ring is read (rare).  The
+// diagonal is adopted as the new Dref only when the previous anchor lies on it too (contig end, indel,
+// rearrangement -- not a chance anchor), so the old chain's high scores neither keep the short cut off for the next
+// 16 anchors nor does one stray anchor derail it.  Stale entries that have left the window only make Mx too large
+// (a missed short cut).
+__global__ void __launch_bounds__(DP_THREADS, 6)
 chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uint16_t *__restrict__ task_n,
              uint32_t *__restrict__ res_all, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
              uint8_t *__restrict__ task_ncand, uint8_t *__restrict__ task_slow) {
@@ -201,16 +220,16 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
     if (w_n == 0) return;
     constexpr int UNR = DP_UNR;
-    static_assert(UNR % 2 == 0 && MAXA % UNR == 0, "anchors are fetched 16 bytes at a time");
-    int Q[LB + UNR], D[LB + UNR], F[LB + UNR];
-    uint32_t RC[LB + UNR];
+    static_assert(UNR % 2 == 0 && MAXA % UNR == 0 && LB % UNR == 0, "anchors are fetched 16 bytes at a time");
+    __shared__ int ringQ[LB][DP_THREADS], ringD[LB][DP_THREADS];
+    __shared__ uint32_t ringFR[LB][DP_THREADS];  // F << 17 | root << 9 | cnt  (0 = empty)
+    __shared__ uint32_t tb_s[ENDS_K][DP_THREADS];  // dynamic indexing without local memory; column per thread
+    int *const rq = &ringQ[0][threadIdx.x], *const rd = &ringD[0][threadIdx.x];
+    uint32_t *const rf = &ringFR[0][threadIdx.x];
 #pragma unroll
-    for (int u = 0; u < LB + UNR; u++) {
-        Q[u] = 0;
-        D[u] = 0;
-        F[u] = NEG_F;  // an empty slot can never win
-        RC[u] = 0;
-    }
+    for (int u = 0; u < LB; u++) rf[u * DP_THREADS] = 0;
+    int Q1 = 0, D1 = 0, F1 = 0, Q2 = 0, D2 = 0, F2 = 0;  // nearest, second nearest predecessor
+    uint32_t RC1 = 0, RC2 = 0;
     const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
     const uint64_t *ap = anc_all + (size_t)tt * MAXA;
     uint32_t *rp = res_all + (size_t)tt * MAXA;
@@ -222,7 +241,6 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     // chunk (rare) hands the task to ends_kernel.  Valid because min_score > (min_anchors - 1) * anchor_score
     // (checked at context creation): an end that reaches min_score has min_anchors anchors, and if the tree's
     // best end does not qualify nothing in the tree does.
-    __shared__ uint32_t tb_s[ENDS_K][DP_THREADS];  // dynamic indexing without local memory; column per thread
     uint32_t *const tb = &tb_s[0][threadIdx.x];
 #pragma unroll
     for (int k = 0; k < ENDS_K; k++) tb[k * DP_THREADS] = 0;
@@ -241,7 +259,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
         }
         if (k == ENDS_K) slow = true;
     };
-    int Mx = NEG_F, Dref = 0;  // short cut state, see below
+    int Mx = 0, Dref = 0;
+    uint32_t off = 0;  // bit d: the d-th previous anchor (0 = nearest) is live and off Dref's diagonal
     const int diag_lim = prm.max_gap + DIAG_SLACK;
     ulonglong2 vnext[UNR / 2];
 #pragma unroll
@@ -257,6 +276,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
 #pragma unroll
             for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR) + x);
         }
+        const int ring0 = (i0 & (LB - 1)) * DP_THREADS;  // slot of anchor i0; anchor i0 + x sits x slots further
         uint32_t outp[UNR];
 #pragma unroll
         for (int x = 0; x < UNR; x++) {
@@ -265,72 +285,75 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             const int qi = (int)an_q(a) + (rev << 20);
             const int Ri = rev ? -(int)an_r(a) : (int)an_r(a);
             const int Di = Ri - qi;
+            const int i = i0 + x;
             int best = prm.anchor_score;
-            uint32_t brc = (uint32_t)(i0 + x) << 9;  // own root, cnt 0 (+1 below)
-            const int me = UNR - 1 - x;               // this anchor's slot
-            const bool live = i0 + x < my_n;
-            auto relax = [&](int sl) {
-                const int dq1 = qi - Q[sl];  // dq - 1
-                const int dd = Di - D[sl];
-                const int dr1 = dd + dq1;    // d_ref - 1
+            uint32_t brc = (uint32_t)i << 9;  // own root, cnt 0 (+1 below)
+            const bool live = i < my_n;
+            auto relax = [&](int Qj, int Dj, int Fj, uint32_t RCj) {
+                const int dq1 = qi - Qj;  // dq - 1
+                const int dd = Di - Dj;
+                const int dr1 = dd + dq1;  // d_ref - 1
                 const int gap = dd < 0 ? -dd : dd;
-                const int cand = F[sl] - gap;
+                const int cand = Fj - gap;
                 if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > best) {
                     best = cand;
-                    brc = RC[sl];
+                    brc = RCj;
                 }
             };
-            relax(me + 1);  // d = 0, the nearest predecessor: ties keep it
-            relax(me + 2);  // d = 1
-            // Short cut.  Colinear anchors (the usual case) chain onto one of the two nearest predecessors with a score
-            // no other one can reach; then the other 14 are not looked at.  (Two, because a chance anchor -- FracMinHash
-            // samples the same 1/125 of k-mer space in both genomes, so ~1.7 % of a pair's anchors are random matches
-            // on a random diagonal -- sits between two anchors of a chain, and the one after it must reach over it.)
-            // Mx bounds what predecessors beyond the nearest two can offer: the largest F among those whose diagonal
-            // lies within max_gap + DIAG_SLACK of Dref, where Dref follows this task's current diagonal to within
-            // DIAG_SLACK.  An anchor further off than that is out of max_gap for this one, and one inside offers
-            // F - gap <= Mx: if Mx <= best nothing replaces `best` (a later predecessor only wins with a strictly
-            // larger candidate) -- the same result as the full scan.  An anchor off the current diagonal gets its own
-            // bound (m2) from the window; the diagonal is adopted as the new Dref only when the previous anchor lies
-            // on it too (contig end, indel, rearrangement -- not a chance anchor), so the old chain's high scores
-            // neither keep the short cut off for the next 16 anchors nor does one stray anchor derail it.  Stale
-            // entries that have left the window only make Mx too large (a missed short cut).
+            relax(Q1, D1, F1, RC1);  // the nearest predecessor: ties keep it
+            relax(Q2, D2, F2, RC2);
             long long dj = (long long)Di - Dref;  // 64-bit: opposite strands are up to 2^32 apart
             dj = dj < 0 ? -dj : dj;
-            const bool jump = live && dj > DIAG_SLACK;
+            bool jump = live && dj > DIAG_SLACK;
             bool settled = !live || Mx <= best;
             if (__any_sync(0xffffffffu, jump)) {
-                int m2 = NEG_F;
-#pragma unroll
-                for (int d = 2; d < LB; d++) {
-                    int dd = D[me + 1 + d] - Di;
-                    dd = dd < 0 ? -dd : dd;
-                    m2 = max(m2, dd <= diag_lim ? F[me + 1 + d] : NEG_F);
+                long long dp = (long long)Di - D1;
+                dp = dp < 0 ? -dp : dp;
+                const bool quick = (off >> 2) == 0 && dj > diag_lim + DIAG_SLACK;
+                int m2 = 0;
+                uint32_t offn = 0;  // `off` relative to this anchor's diagonal, entries beyond the nearest two
+                if (__any_sync(0xffffffffu, jump && !quick)) {
+#pragma unroll 1
+                    for (int d = 2; d < LB; d++) {
+                        const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
+                        const uint32_t fr = rf[sl];
+                        long long dd = (long long)rd[sl] - Di;
+                        dd = dd < 0 ? -dd : dd;
+                        if (dd <= diag_lim) m2 = max(m2, (int)(fr >> 17));
+                        if (fr && dd > DIAG_SLACK) offn |= 1u << d;
+                    }
                 }
                 if (jump) {
-                    settled = m2 <= best;
-                    long long dp = (long long)Di - D[me + 1];
-                    dp = dp < 0 ? -dp : dp;
+                    settled = m2 <= best;  // quick: m2 = 0
                     if (dp <= DIAG_SLACK) {  // the previous anchor is on this diagonal too: follow it
                         Mx = m2;
                         Dref = Di;
+                        if (quick) offn = 0xfffcu & ((1u << (i < LB ? i : LB)) - 1u);  // all the old diagonal's entries
+                        long long d2 = (long long)D2 - Di;
+                        d2 = d2 < 0 ? -d2 : d2;
+                        off = offn | ((F2 != 0 && d2 > DIAG_SLACK) ? 2u : 0u);
+                        jump = false;
                     }
                 }
             }
             if (!__all_sync(0xffffffffu, settled)) {
-#pragma unroll
-                for (int d = 2; d < LB; d++) relax(me + 1 + d);
+#pragma unroll 1
+                for (int d = 2; d < LB; d++) {
+                    const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
+                    const uint32_t fr = rf[sl];
+                    relax(rq[sl], rd[sl], (int)(fr >> 17), fr & 0x1ffffu);
+                }
             }
             {  // the second nearest predecessor is beyond the nearest two of the next anchor
-                int dd = D[me + 2] - Dref;
+                int dd = D2 - Dref;
                 dd = dd < 0 ? -dd : dd;
-                Mx = max(Mx, dd <= diag_lim ? F[me + 2] : NEG_F);
+                Mx = max(Mx, dd <= diag_lim ? F2 : 0);
             }
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;
             if (live && best >= prm.min_score && (int)(rci & 0x1ffu) >= prm.min_anchors) {
                 const uint32_t root = rci >> 9;
-                const uint32_t e = ((uint32_t)best << 16) | ((uint32_t)(MAXA - 1 - (i0 + x)) << 8) | root;
+                const uint32_t e = ((uint32_t)best << 16) | ((uint32_t)(MAXA - 1 - i) << 8) | root;
                 if (root == cur_root)
                     cur_e = cur_e > e ? cur_e : e;
                 else {
@@ -339,22 +362,17 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                     cur_e = e;
                 }
             }
-            Q[me] = qi + 1;
-            D[me] = Di;
-            F[me] = live ? best + prm.anchor_score : NEG_F;
-            RC[me] = rci;
+            Q2 = Q1, D2 = D1, F2 = F1, RC2 = RC1;
+            Q1 = qi + 1, D1 = Di, F1 = live ? best + prm.anchor_score : 0, RC1 = rci;
+            rq[ring0 + x * DP_THREADS] = Q1;
+            rd[ring0 + x * DP_THREADS] = D1;
+            rf[ring0 + x * DP_THREADS] = live ? outp[x] + ((uint32_t)prm.anchor_score << 17) : 0u;
+            off = ((off << 1) | (jump ? 1u : 0u)) & 0xffffu;
         }
         if (i0 < my_n) {
 #pragma unroll
             for (int x = 0; x < UNR / 2; x++)
                 __stcg(reinterpret_cast<uint2 *>(rp + i0) + x, make_uint2(outp[2 * x], outp[2 * x + 1]));
-        }
-#pragma unroll
-        for (int u = LB + UNR - 1; u >= UNR; u--) {
-            Q[u] = Q[u - UNR];
-            D[u] = D[u - UNR];
-            F[u] = F[u - UNR];
-            RC[u] = RC[u - UNR];
         }
     }
     // ---- the chunk's top candidates, by (score desc, q0, r0), into the task's slots
@@ -552,6 +570,115 @@ ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_al
     }
 }
 
+
+// A chain as the selection sees it: one 32-byte record in its PAIR's list (the pair's chunks' candidates back to back
+// in no particular order), with everything the result needs precomputed -- the finalize kernels touch no other table.
+struct __align__(16) PCand {
+    uint32_t q0, q1, r0, r1;
+    uint16_t score, n_anchors, n_seeds, ext;  // ext: bases the clipped extension adds to both spans
+    uint32_t key2;                            // chunk << 4 | ordinal: rank among equal scores
+    uint32_t pad;
+};
+static_assert(sizeof(PCand) == 32, "pcand size");
+
+// Clipped extension of an accepted chain's spans, left + right (the spans themselves are q1-q0+k and r1-r0+k).
+__device__ __forceinline__ uint32_t cand_ext(const DbView &db, const AniParams &prm, const Cand &c, uint32_t choff,
+                                             uint32_t rcoff, int nrc) {
+    const long long e = prm.span_ext, k1 = K_SEED - 1;
+    const long long cs = db.chunk_start[choff + c.chunk], ce = cs + db.chunk_len[choff + c.chunk] - 1;
+    int lo = 0, hi = nrc - 1;  // reference contig holding r0
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (db.ctg_pstart[rcoff + mid] <= c.r0)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const long long rs = db.ctg_pstart[rcoff + lo], re = rs + db.ctg_len[rcoff + lo] - 1;
+    const long long a0 = (long long)c.q0 - k1, a1 = c.q1, b0 = (long long)c.r0 - k1, b1 = c.r1;
+    const long long room_ql = a0 - cs, room_qr = ce - a1, room_rlo = b0 - rs, room_rhi = re - b1;
+    // an extension stops where either genome runs out; a reverse chain's left query end faces the reference's high end
+    long long el = c.rev ? room_rhi : room_rlo, er = c.rev ? room_rlo : room_rhi;
+    el = el < room_ql ? el : room_ql;
+    er = er < room_qr ? er : room_qr;
+    el = el < e ? el : e;
+    er = er < e ? er : e;
+    el = el < 0 ? 0 : el;
+    er = er < 0 ? 0 : er;
+    return (uint32_t)(el + er);
+}
+
+// One thread per task: its candidates (chain_kernel / ends_kernel left them in the task's slots) move to the batch's
+// compact list at cand_off[t] (exclusive scan of the tasks' candidate counts): a pair's candidates are contiguous, in
+// (chunk, ordinal) order, and cand_off brackets them.  The extension is worked out here, at full occupancy -- the
+// contig search is a chain of dependent loads that a warp-per-pair kernel cannot hide.
+__global__ void cand_pack_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, uint32_t n_tasks,
+                                 const uint32_t *__restrict__ task_pair, const uint8_t *__restrict__ task_ncand,
+                                 const uint32_t *__restrict__ cand_off, const Cand *__restrict__ gcands,
+                                 PCand *__restrict__ pcands) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    const uint32_t c = task_ncand[t];
+    if (c == 0) return;
+    const PairInfo pi = info[task_pair[t]];
+    const uint32_t choff = db.g_chunk_off[pi.q], rcoff = db.g_ctg_off[pi.r];
+    const int nrc = (int)(db.g_ctg_off[pi.r + 1] - rcoff);
+    PCand *dst = pcands + cand_off[t];
+    for (uint32_t x = 0; x < c; x++) {
+        const Cand cd = gcands[(size_t)t * SLOTS + x];
+        PCand o;
+        o.q0 = cd.q0, o.q1 = cd.q1, o.r0 = cd.r0, o.r1 = cd.r1;
+        o.score = cd.score, o.n_anchors = cd.n_anchors, o.n_seeds = cd.n_seeds;
+        o.ext = (uint16_t)cand_ext(db, prm, cd, choff, rcoff, nrc);
+        o.key2 = (cd.chunk << 4) | cd.ordinal;
+        o.pad = 0;
+        dst[x] = o;
+    }
+}
+
+// The pair's result from the sums over its accepted chains (one thread).
+__device__ __forceinline__ PairOut make_pair_out(const DbView &db, const AniParams &prm, const PairInfo &pi, int64_t t_a,
+                                                 int64_t t_s, int64_t t_span_q, int64_t t_span_r, int n_acc) {
+    PairOut o;
+    o.ani = o.ani_raw = -1.0;
+    o.af_q = o.af_r = 0.0;
+    o.n_anchors = t_a;
+    o.n_seeds = t_s;
+    o.span_q = t_span_q;
+    o.span_r = t_span_r;
+    o.n_chains = n_acc;
+    o.swapped = (int32_t)pi.swapped;
+    // the two end anchors of every chain are anchors by construction: left out of both counts (oracle ora_pair)
+    const int64_t a_in = o.n_anchors - 2 * (int64_t)o.n_chains, s_in = o.n_seeds - 2 * (int64_t)o.n_chains;
+    if (a_in > 0 && s_in > 0) {
+        double ratio = (double)a_in / (double)s_in;
+        if (ratio > 1.0) ratio = 1.0;
+        const double mean = pow(ratio, 1.0 / (double)K_SEED);
+        o.ani_raw = mean;
+        double afq = (double)o.span_q / (double)db.g_total_len[pi.q];
+        double afr = (double)o.span_r / (double)db.g_total_len[pi.r];
+        o.af_q = afq > 1.0 ? 1.0 : afq;
+        o.af_r = afr > 1.0 ? 1.0 : afr;
+        const double x = 100.0 * (1.0 - mean);
+        double ani = 1.0;
+        if (x > 0.0) {
+            ani = 1.0 - prm.debias_a * pow(x, prm.debias_g) / 100.0;
+            if (ani < 0.0) ani = 0.0;
+        }
+        o.ani = ani > 1.0 ? 1.0 : ani;
+    }
+    return o;
+}
+
+// does the earlier-ranked chain `d` (q0 q1 r0 r1) overlap more than ovl_num/ovl_den of chain `c`'s own length, on the
+// query or on the reference?
+__device__ __forceinline__ bool chain_blocks(const uint4 &d, const uint4 &c, const AniParams &prm) {
+    const long long lq = (long long)c.y - c.x + 1, lr = (long long)c.w - c.z + 1;
+    const long long oq = (long long)(c.y < d.y ? c.y : d.y) - (long long)(c.x > d.x ? c.x : d.x) + 1;
+    const long long orr = (long long)(c.w < d.w ? c.w : d.w) - (long long)(c.z > d.z ? c.z : d.z) + 1;
+    return (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) || (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
+}
+
 __device__ __forceinline__ double block_sum(double v, double *scratch /* [FIN_THREADS/32] */, int tid) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
@@ -568,83 +695,242 @@ struct FinCtl {
     double red[FIN_THREADS / 32];
 };
 
-// Candidates a pair brings to the selection (sum of its chunks' candidate counts).  Pairs with at most MAXP go
-// through the shared-memory finalize kernel, whose launch is sized for the largest of them in the batch
-// (max_small); the others -- a query of thousands of contigs against a close relative -- are listed for the
-// global-memory instance (finalize_kernel<true>): no pair is ever dropped or capped.
-__global__ void pair_ncand_kernel(const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off, uint32_t base,
-                                  int64_t n_pairs, const uint8_t *__restrict__ task_ncand, uint32_t *__restrict__ pair_nc,
-                                  uint32_t *ctl /* [0] max over small pairs, [1] number of big pairs */,
-                                  uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_nc) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const uint32_t t0 = task_off[p] - base, nch = info[p].nch;
-    uint32_t nc = 0;
-    for (uint32_t ch = 0; ch < nch; ch++) nc += task_ncand[t0 + ch];
-    pair_nc[p] = nc;
-    if (nc <= (uint32_t)MAXP)
-        atomicMax(&ctl[0], nc);
-    else {
-        const uint32_t k = atomicAdd(&ctl[1], 1u);
-        big_list[k] = (uint32_t)p;
-        big_nc[k] = nc;
+// Selection + ANI/AF, common case: ONE WARP per pair, no block barriers.  Input: the pair's PCand list
+// (cand_pack_kernel): records cand_off[t0] .. cand_off[t0 + nch] of pcands, in (chunk, ordinal) order.
+//   A chain can only be blocked by a chain it TOUCHES (on the query or on the reference), and almost none touch:
+//   query : chunks are disjoint on the query, so only the (<= SLOTS) chains of one chunk can touch there -- they are
+//           neighbours in the list, each is tested against the earlier ordinals of its chunk (on both axes);
+//   ref   : the list is ordered by r0 -- a warp bitonic sort of (r0 << 32 | index) in shared memory, skipped when the
+//           list is already in that order (colinear genomes) -- and every chain walks its successors while they start
+//           at or before its own end: normally none.
+//   Touching chains of which the earlier-RANKED one (score desc, chunk, ordinal) covers more than ovl of the later one
+//   go to an edge list; a chain is rejected iff an ACCEPTED earlier-ranked chain blocks it -- rounds over the edge
+//   list only.  Then the accepted chains' anchors / seeds / spans are summed (integers) and one thread writes the result.
+// Pairs with more than `wcap` candidates or more than FW_EDGES blocking relations are listed for the CTA-per-pair
+// kernels below (shared memory up to MAXP candidates, global scratch beyond): no pair is ever dropped or capped.
+constexpr int FW_WARPS = 4;     // warps (pairs in flight) per CTA
+constexpr int FW_EDGES = 256;   // blocking relations per pair the warp kernel resolves itself
+__host__ __device__ constexpr size_t fw_bytes_per_warp(uint32_t wcap /* power of two */) {
+    return (size_t)wcap * (8 + 1) + (size_t)FW_EDGES * 4 + 16;
+}
+
+__device__ __forceinline__ bool ranks_before(uint32_t score_a, uint32_t key2_a, uint32_t score_b, uint32_t key2_b) {
+    return score_a > score_b || (score_a == score_b && key2_a < key2_b);
+}
+
+// list entries i and j touch: if one blocks the other, append (earlier-ranked << 16 | later-ranked)
+__device__ __forceinline__ void fw_edge(const PCand *__restrict__ list, int i, int j, const AniParams &prm, uint32_t *edges,
+                                        uint32_t *n_edges) {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(list + i)), b = __ldcg(reinterpret_cast<const uint4 *>(list + j));
+    const uint4 a1 = __ldcg(reinterpret_cast<const uint4 *>(list + i) + 1), b1 = __ldcg(reinterpret_cast<const uint4 *>(list + j) + 1);
+    const bool i_first = ranks_before(a1.x & 0xffffu, a1.z, b1.x & 0xffffu, b1.z);
+    const bool blocks = i_first ? chain_blocks(a, b, prm) : chain_blocks(b, a, prm);
+    if (!blocks) return;
+    const uint32_t e = atomicAdd(n_edges, 1u);
+    if (e < (uint32_t)FW_EDGES) edges[e] = i_first ? ((uint32_t)i << 16) | (uint32_t)j : ((uint32_t)j << 16) | (uint32_t)i;
+}
+
+// ctl: [0] largest candidate count among the listed mid pairs, [1] number of big pairs, [2] number of mid pairs
+__global__ void __launch_bounds__(FW_WARPS * 32)
+finalize_warp_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
+                     uint32_t base, int64_t n_pairs, const PCand *__restrict__ pcands, const uint32_t *__restrict__ cand_off,
+                     const uint32_t *__restrict__ perm, PairOut *__restrict__ out, uint32_t wcap, uint32_t *ctl,
+                     uint32_t *__restrict__ mid_list, uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_nc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *my = smem + (size_t)warp * ((fw_bytes_per_warp(wcap) + 15) & ~(size_t)15);
+    uint64_t *key = reinterpret_cast<uint64_t *>(my);                           // [wcap] r0 << 32 | list index
+    uint32_t *edges = reinterpret_cast<uint32_t *>(my + (size_t)wcap * 8);      // [FW_EDGES] (earlier rank << 16) | later
+    uint32_t *n_edges = edges + FW_EDGES;                                       // [1] (+ 3 pad)
+    uint8_t *state = reinterpret_cast<uint8_t *>(n_edges + 4);                  // [wcap] low 2 bits: 0 undecided, 1 accepted, 2 rejected
+    const int64_t warps_total = (int64_t)gridDim.x * FW_WARPS;
+    for (int64_t p = (int64_t)blockIdx.x * FW_WARPS + warp; p < n_pairs; p += warps_total) {
+        const PairInfo pi = info[p];
+        const uint32_t t0 = task_off[p] - base;
+        const uint32_t c0 = cand_off[t0], nc = cand_off[t0 + pi.nch] - c0;
+        if (nc > wcap) {
+            if (lane == 0) {
+                if (nc <= (uint32_t)MAXP) {
+                    atomicMax(&ctl[0], nc);
+                    mid_list[atomicAdd(&ctl[2], 1u)] = (uint32_t)p;
+                } else {
+                    const uint32_t k = atomicAdd(&ctl[1], 1u);
+                    big_list[k] = (uint32_t)p;
+                    big_nc[k] = nc;
+                }
+            }
+            continue;
+        }
+        const PCand *list = pcands + c0;
+        const int n = (int)nc;
+        int m = 32;
+        while (m < n) m <<= 1;
+        // ---- keys; is the list already ordered by r0?
+        bool ordered = true;
+        for (int t = lane; t < m; t += 32) {
+            uint64_t k = ~0ull;
+            if (t < n) {
+                const uint32_t r0 = __ldcg(&list[t].r0);
+                k = ((uint64_t)r0 << 32) | (uint32_t)t;
+                state[t] = 1;
+            }
+            key[t] = k;
+            const uint64_t prev = __shfl_up_sync(0xffffffffu, k, 1);
+            if (lane > 0 && prev > k) ordered = false;
+        }
+        if (lane == 0) *n_edges = 0;
+        __syncwarp();
+        for (int t = 32 + lane; t < n; t += 32)  // across the rows of 32
+            if (lane == 0 && key[t - 1] > key[t]) ordered = false;
+        if (!__all_sync(0xffffffffu, ordered)) {
+            for (int k = 2; k <= m; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (m >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int q = i | j;
+                        const bool up = (i & k) == 0;
+                        const uint64_t a = key[i], b = key[q];
+                        if ((a > b) == up) {
+                            key[i] = b;
+                            key[q] = a;
+                        }
+                    }
+                    __syncwarp();
+                }
+        }
+        // ---- touching chains: later ordinals of the same chunk (any axis), successors in r0 order (reference)
+        for (int t = lane; t < n; t += 32) {
+            const uint32_t k2 = __ldcg(&list[t].key2);
+            const int ord = (int)(k2 & 15u);
+            if (ord) {  // rare
+                const uint4 c = __ldcg(reinterpret_cast<const uint4 *>(list + t));
+                for (int u = t - ord; u < t; u++) {
+                    const uint4 d = __ldcg(reinterpret_cast<const uint4 *>(list + u));
+                    if ((d.x <= c.y && c.x <= d.y) || (d.z <= c.w && c.z <= d.w)) fw_edge(list, u, t, prm, edges, n_edges);
+                }
+            }
+        }
+        for (int s = lane; s < n; s += 32) {
+            const int i = (int)(key[s] & 0xffffu);
+            const uint32_t r1 = __ldcg(&list[i].r1);
+            for (int u = s + 1; u < n && (uint32_t)(key[u] >> 32) <= r1; u++) {  // rare
+                const int j = (int)(key[u] & 0xffffu);
+                if ((__ldcg(&list[i].key2) >> 4) != (__ldcg(&list[j].key2) >> 4)) fw_edge(list, i, j, prm, edges, n_edges);
+            }
+        }
+        __syncwarp();
+        const uint32_t ne = *n_edges;
+        if (ne > (uint32_t)FW_EDGES) {  // rare: the CTA kernel takes the pair
+            if (lane == 0) {
+                atomicMax(&ctl[0], nc);
+                mid_list[atomicAdd(&ctl[2], 1u)] = (uint32_t)p;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (ne) {
+            for (uint32_t e = lane; e < ne; e += 32) state[edges[e] & 0xffffu] = 0;
+            __syncwarp();
+            // state of a blocked chain: bit 2 = an accepted chain blocks it, bit 3 = an undecided one might
+            for (;;) {
+                for (uint32_t e = lane; e < ne; e += 32) {
+                    const uint32_t lo = edges[e] >> 16, hi = edges[e] & 0xffffu;
+                    if ((state[hi] & 3) == 0) {
+                        const uint8_t s = state[lo] & 3;
+                        if (s == 1) atomicOr(reinterpret_cast<unsigned int *>(state + (hi & ~3u)), 4u << (8 * (hi & 3u)));
+                        if (s == 0) atomicOr(reinterpret_cast<unsigned int *>(state + (hi & ~3u)), 8u << (8 * (hi & 3u)));
+                    }
+                }
+                __syncwarp();
+                bool open = false;
+                for (uint32_t e = lane; e < ne; e += 32) {
+                    const uint32_t hi = edges[e] & 0xffffu;
+                    const uint8_t s = state[hi];
+                    if ((s & 3) == 0) {
+                        // several edges may share `hi`: they all compute the same value from the same flags
+                        if (s & 4) state[hi] = 2;
+                        else if (!(s & 8)) state[hi] = 1;
+                        else open = true;
+                    }
+                }
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, open)) break;
+                for (uint32_t e = lane; e < ne; e += 32) {  // undecided chains start the next round with clean flags
+                    const uint32_t hi = edges[e] & 0xffffu;
+                    if ((state[hi] & 3) == 0) state[hi] = 0;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- sums over the accepted chains
+        uint32_t s_q = 0, s_r = 0, s_a = 0, s_s = 0, n_acc = 0;  // a lane sums <= wcap/32 spans: far below 2^32
+        for (int t = lane; t < n; t += 32) {
+            if ((state[t] & 3) != 1) continue;
+            const uint4 w0 = __ldcg(reinterpret_cast<const uint4 *>(list + t));
+            const uint2 w1 = __ldcg(reinterpret_cast<const uint2 *>(list + t) + 2);  // score n_anchors | n_seeds ext
+            const uint32_t ext = w1.y >> 16;
+            s_q += w0.y - w0.x + (uint32_t)K_SEED + ext;
+            s_r += w0.w - w0.z + (uint32_t)K_SEED + ext;
+            s_a += w1.x >> 16;
+            s_s += w1.y & 0xffffu;
+            n_acc++;
+        }
+        unsigned long long t_q = s_q, t_r = s_r;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            t_q += __shfl_down_sync(0xffffffffu, t_q, d);
+            t_r += __shfl_down_sync(0xffffffffu, t_r, d);
+        }
+        s_a = __reduce_add_sync(0xffffffffu, s_a);
+        s_s = __reduce_add_sync(0xffffffffu, s_s);
+        n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+        if (lane == 0) out[perm[p]] = make_pair_out(db, prm, pi, (int64_t)s_a, (int64_t)s_s, (int64_t)t_q, (int64_t)t_r, (int)n_acc);
+        __syncwarp();
     }
 }
 
-constexpr size_t FIN_BYTES_PER_CAND = sizeof(Cand) + 8 + 1;  // candidate + sort key + state
+constexpr size_t FIN_BYTES_PER_CAND = sizeof(PCand) + 8 + 1;  // candidate + sort key + state
 
 // sort key of a candidate: score desc, chunk, ordinal within the chunk (= (q0, r0) order), then its slot
 //   (8191 - score)(13) << 51 | chunk(23) << 28 | ordinal(4) << 24 | slot(24)
 constexpr uint32_t FIN_IDX_MASK = 0xffffffu;
 constexpr uint32_t MAX_CHUNKS_PER_GENOME = 1u << 23;
 
-// BIG = false: one CTA per pair of the batch, candidates / keys / states in dynamic shared memory sized for `cap`
-//   candidates (a power of two >= the batch's largest small pair): Cand[cap] | u64 key[cap] | u8 state[cap].
-// BIG = true: one CTA per listed pair, the same three arrays in global scratch at big_off[blockIdx.x] (bytes),
-//   capacity big_cap[blockIdx.x].
+// The pairs finalize_warp_kernel listed: one CTA per listed pair.
+// BIG = false: candidates / keys / states in dynamic shared memory sized for `cap` candidates (a power of two >= the
+//   largest listed pair): PCand[cap] | u64 key[cap] | u8 state[cap].
+// BIG = true: the same three arrays in global scratch at big_off[blockIdx.x] (bytes), capacity big_cap[blockIdx.x].
 template <bool BIG>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, const uint32_t *__restrict__ task_off,
-                uint32_t base, int64_t n_pairs, const Cand *__restrict__ gcands, const uint8_t *__restrict__ task_ncand,
-                const uint32_t *__restrict__ pair_nc, const uint32_t *__restrict__ perm, PairOut *__restrict__ out,
-                uint32_t cap, const uint32_t *__restrict__ big_list, const unsigned long long *__restrict__ big_off,
+                uint32_t base, int64_t n_pairs, const PCand *__restrict__ pcands, const uint32_t *__restrict__ cand_off,
+                const uint32_t *__restrict__ perm, PairOut *__restrict__ out,
+                uint32_t cap, const uint32_t *__restrict__ list, const unsigned long long *__restrict__ big_off,
                 const uint32_t *__restrict__ big_cap, unsigned char *__restrict__ big_scratch) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FinCtl ctl;
     const int tid = threadIdx.x;
-    int64_t p = blockIdx.x;
+    const int64_t p = list[blockIdx.x];
     unsigned char *buf = smem;
     if (BIG) {
-        p = big_list[blockIdx.x];
         cap = big_cap[blockIdx.x];
         buf = big_scratch + big_off[blockIdx.x];
     }
     if (p >= n_pairs) return;
-    const int nc = (int)pair_nc[p];
-    if (!BIG && nc > MAXP) return;  // finalize_kernel<true> does this pair
-    Cand *cands = reinterpret_cast<Cand *>(buf);
-    uint64_t *skey = reinterpret_cast<uint64_t *>(buf + sizeof(Cand) * (size_t)cap);
-    uint8_t *state = buf + (sizeof(Cand) + 8) * (size_t)cap;
     const PairInfo pi = info[p];
-    const uint32_t nch = pi.nch, t0 = task_off[p] - base;
-    const uint32_t choff = db.g_chunk_off[pi.q];
-    if (tid == 0) ctl.n_cand = 0;
-    __syncthreads();
-    for (uint32_t ch = tid; ch < nch; ch += FIN_THREADS) {
-        const int c = task_ncand[t0 + ch];
-        if (c) {
-            const int at = atomicAdd(&ctl.n_cand, c);
-            for (int x = 0; x < c; x++) cands[at + x] = gcands[(size_t)(t0 + ch) * SLOTS + x];
-        }
-    }
-    __syncthreads();
+    const uint32_t t0 = task_off[p] - base;
+    const PCand *src = pcands + cand_off[t0];
+    const int nc = (int)(cand_off[t0 + pi.nch] - cand_off[t0]);
+    PCand *cands = reinterpret_cast<PCand *>(buf);
+    uint64_t *skey = reinterpret_cast<uint64_t *>(buf + sizeof(PCand) * (size_t)cap);
+    uint8_t *state = buf + (sizeof(PCand) + 8) * (size_t)cap;
     int m = 1;
     while (m < nc) m <<= 1;
     for (int i = tid; i < m; i += FIN_THREADS) {
         if (i < nc) {
-            const Cand &c = cands[i];
-            skey[i] = ((uint64_t)(8191u - c.score) << 51) | ((uint64_t)c.chunk << 28) | ((uint64_t)c.ordinal << 24) |
-                      (uint64_t)i;
+            const PCand c = src[i];
+            cands[i] = c;
+            skey[i] = ((uint64_t)(8191u - c.score) << 51) | ((uint64_t)c.key2 << 24) | (uint64_t)i;
         } else
             skey[i] = ~0ull;
         state[i] = 0;
@@ -679,7 +965,6 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
                 if (side && t == w0) break;
                 if (state[t]) continue;
                 const uint4 cr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[t] & FIN_IDX_MASK)]);  // q0 q1 r0 r1
-                const long long lq = (long long)cr.y - cr.x + 1, lr = (long long)cr.w - cr.z + 1;
                 int verdict = 1;
                 for (int u = 0; u < t; u++) {
                     const uint4 dr = *reinterpret_cast<const uint4 *>(&cands[(int)(skey[u] & FIN_IDX_MASK)]);
@@ -688,11 +973,7 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
                     if (!tq && !tr) continue;
                     const uint8_t su = ((volatile uint8_t *)state)[u];
                     if (su == 2) continue;
-                    const long long oq = (long long)(cr.y < dr.y ? cr.y : dr.y) - (long long)(cr.x > dr.x ? cr.x : dr.x) + 1;
-                    const long long orr = (long long)(cr.w < dr.w ? cr.w : dr.w) - (long long)(cr.z > dr.z ? cr.z : dr.z) + 1;
-                    const bool blocks = (oq > 0 && oq * prm.ovl_den > lq * prm.ovl_num) ||
-                                        (orr > 0 && orr * prm.ovl_den > lr * prm.ovl_num);
-                    if (!blocks) continue;
+                    if (!chain_blocks(dr, cr, prm)) continue;
                     if (su == 1) {
                         verdict = 2;
                         break;
@@ -708,75 +989,23 @@ finalize_kernel(DbView db, AniParams prm, const PairInfo *__restrict__ info, con
         __syncthreads();
         if (!ctl.unresolved) break;
     }
-    // accumulate accepted chains: anchors / seeds (pooled), spans with the symmetric clipped extension
-    const uint32_t rcoff = db.g_ctg_off[pi.r];
-    const int nrc = (int)(db.g_ctg_off[pi.r + 1] - rcoff);
+    // accumulate accepted chains: anchors / seeds (pooled), spans with the clipped extension
     int n_acc_local = 0;
     double l_span_q = 0, l_span_r = 0, l_a = 0, l_s = 0;  // exact in double (< 2^53); reduced below, no atomics
     for (int t = tid; t < nc; t += FIN_THREADS) {
         if (state[t] != 1) continue;
         n_acc_local++;
-        const Cand &c = cands[(int)(skey[t] & FIN_IDX_MASK)];
-        const long long e = prm.span_ext, k1 = K_SEED - 1;
-        const long long cs = db.chunk_start[choff + c.chunk], ce = cs + db.chunk_len[choff + c.chunk] - 1;
-        int lo = 0, hi = nrc - 1;  // reference contig holding r0
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (db.ctg_pstart[rcoff + mid] <= c.r0)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        const long long rs = db.ctg_pstart[rcoff + lo], re = rs + db.ctg_len[rcoff + lo] - 1;
-        const long long a0 = (long long)c.q0 - k1, a1 = c.q1, b0 = (long long)c.r0 - k1, b1 = c.r1;
-        const long long room_ql = a0 - cs, room_qr = ce - a1, room_rlo = b0 - rs, room_rhi = re - b1;
-        // an extension stops where either genome runs out; a reverse chain's left query end faces the reference's high end
-        long long el = c.rev ? room_rhi : room_rlo, er = c.rev ? room_rlo : room_rhi;
-        el = el < room_ql ? el : room_ql;
-        er = er < room_qr ? er : room_qr;
-        el = el < e ? el : e;
-        er = er < e ? er : e;
-        el = el < 0 ? 0 : el;
-        er = er < 0 ? 0 : er;
-        l_span_q += (double)(a1 - a0 + 1 + el + er);
-        l_span_r += (double)(b1 - b0 + 1 + el + er);
+        const PCand &c = cands[(int)(skey[t] & FIN_IDX_MASK)];
+        l_span_q += (double)(c.q1 - c.q0 + (uint32_t)K_SEED + c.ext);
+        l_span_r += (double)(c.r1 - c.r0 + (uint32_t)K_SEED + c.ext);
         l_a += (double)c.n_anchors;
         l_s += (double)c.n_seeds;
     }
     const double t_span_q = block_sum(l_span_q, ctl.red, tid), t_span_r = block_sum(l_span_r, ctl.red, tid);
     const double t_a = block_sum(l_a, ctl.red, tid), t_s = block_sum(l_s, ctl.red, tid);
     const double t_acc = block_sum((double)n_acc_local, ctl.red, tid);
-    if (tid == 0) {
-        PairOut o;
-        o.ani = o.ani_raw = -1.0;
-        o.af_q = o.af_r = 0.0;
-        o.n_anchors = (int64_t)t_a;
-        o.n_seeds = (int64_t)t_s;
-        o.span_q = (int64_t)t_span_q;
-        o.span_r = (int64_t)t_span_r;
-        o.n_chains = (int)t_acc;
-        o.swapped = (int32_t)pi.swapped;
-        // the two end anchors of every chain are anchors by construction: left out of both counts (oracle ora_pair)
-        const int64_t a_in = o.n_anchors - 2 * (int64_t)o.n_chains, s_in = o.n_seeds - 2 * (int64_t)o.n_chains;
-        if (a_in > 0 && s_in > 0) {
-            double ratio = (double)a_in / (double)s_in;
-            if (ratio > 1.0) ratio = 1.0;
-            const double mean = pow(ratio, 1.0 / (double)K_SEED);
-            o.ani_raw = mean;
-            double afq = (double)o.span_q / (double)db.g_total_len[pi.q];
-            double afr = (double)o.span_r / (double)db.g_total_len[pi.r];
-            o.af_q = afq > 1.0 ? 1.0 : afq;
-            o.af_r = afr > 1.0 ? 1.0 : afr;
-            const double x = 100.0 * (1.0 - mean);
-            double ani = 1.0;
-            if (x > 0.0) {
-                ani = 1.0 - prm.debias_a * pow(x, prm.debias_g) / 100.0;
-                if (ani < 0.0) ani = 0.0;
-            }
-            o.ani = ani > 1.0 ? 1.0 : ani;
-        }
-        out[perm[p]] = o;
-    }
+    if (tid == 0)
+        out[perm[p]] = make_pair_out(db, prm, pi, (int64_t)t_a, (int64_t)t_s, (int64_t)t_span_q, (int64_t)t_span_r, (int)t_acc);
 }
 
 // K5 -- edge compaction: keep pairs with an estimate and max(AF) >= min_af; percent units.  Order-preserving

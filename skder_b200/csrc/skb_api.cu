@@ -217,6 +217,18 @@ void exclusive_scan_u32(skb_ctx *c, const uint32_t *in, uint32_t *out, size_t n)
     c->launches += 2;
 }
 
+__global__ void widen_u8_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+// out[i] = sum of in[0..i), in place over the widened copy
+void exclusive_scan_u8(skb_ctx *c, const uint8_t *in, uint32_t *out, size_t n) {
+    widen_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(in, out, n);
+    CK(cudaGetLastError());
+    c->launches++;
+    exclusive_scan_u32(c, out, out, n);
+}
+
 void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int end_bit = 64) {
     size_t bytes = 0;
     CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int64_t)n, 0, end_bit, c->st));
@@ -341,9 +353,19 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     c->anchor_ev_used = 0;
     if (n_pairs == 0) return;
     if (n_pairs >= (1ll << 31)) throw CudaFail{"too many surviving pairs in one call"};
+    // candidates per pair the warp-per-pair finalize kernel keeps in shared memory (a multiple of 32)
+    static const uint32_t fw_cap = [] {
+        const char *e = std::getenv("SKB_FW_CAP");
+        const int v = e ? atoi(e) : 1024;
+        uint32_t w = 32;
+        while ((int)w < v && w < 4096) w <<= 1;  // a power of two: the bitonic network's size
+        return w;
+    }();
+    const size_t fw_smem = (size_t)FW_WARPS * ((fw_bytes_per_warp(fw_cap) + 15) & ~(size_t)15);
     if (!c->ani_attr_set) {
         CK(cudaFuncSetAttribute(finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(FIN_BYTES_PER_CAND * MAXP)));
+        CK(cudaFuncSetAttribute(finalize_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw_smem));
         c->ani_attr_set = true;
     }
     const DbView view = c->view();
@@ -416,22 +438,27 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         cap_pairs = std::max(cap_pairs, bt.p1 - bt.p0);
     }
     PoolRef<uint64_t> b_anc(c->pool["ani.anc"]);
-    PoolRef<uint32_t> b_res(c->pool["ani.res"]), b_next(c->pool["ani.next"]), b_pair_nc(c->pool["ani.pair_nc"]),
-        b_fctl(c->pool["ani.fin_ctl"]), b_big_list(c->pool["ani.big_list"]), b_big_nc(c->pool["ani.big_nc"]);
+    PoolRef<uint32_t> b_res(c->pool["ani.res"]), b_next(c->pool["ani.next"]), b_fctl(c->pool["ani.fin_ctl"]),
+        b_big_list(c->pool["ani.big_list"]), b_big_nc(c->pool["ani.big_nc"]), b_mid_list(c->pool["ani.mid_list"]);
     PoolRef<uint16_t> b_tn(c->pool["ani.tn"]);
     PoolRef<TaskDesc> b_desc(c->pool["ani.desc"]);
     PoolRef<Cand> b_cands(c->pool["ani.cands"]);
+    PoolRef<PCand> b_pcands(c->pool["ani.pcands"]);
+    PoolRef<uint32_t> b_task_pair(c->pool["ani.task_pair"]), b_cand_off(c->pool["ani.cand_off"]);
     PoolRef<uint8_t> b_ncand(c->pool["ani.ncand"]), b_slow(c->pool["ani.slow"]);
     b_anc.reserve((size_t)cap * MAXA + 2, 0, c->st);
     b_res.reserve((size_t)cap * MAXA, 0, c->st);
     b_tn.reserve((size_t)cap, 0, c->st);
     b_desc.reserve((size_t)cap, 0, c->st);
     b_cands.reserve((size_t)cap * SLOTS, 0, c->st);
-    b_ncand.reserve((size_t)cap, 0, c->st);
+    b_pcands.reserve((size_t)cap * SLOTS, 0, c->st);
+    b_task_pair.reserve((size_t)cap, 0, c->st);
+    b_cand_off.reserve((size_t)cap + 1, 0, c->st);
+    b_ncand.reserve((size_t)cap + 1, 0, c->st);
     b_slow.reserve((size_t)cap, 0, c->st);
     b_next.reserve(1, 0, c->st);
-    b_pair_nc.reserve((size_t)cap_pairs, 0, c->st);
-    b_fctl.reserve(2, 0, c->st);
+    b_fctl.reserve(4, 0, c->st);
+    b_mid_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_nc.reserve((size_t)cap_pairs, 0, c->st);
     static const bool trace = std::getenv("SKB_TRACE") != nullptr;  // diagnosis: per-kernel timeline on stderr
@@ -451,13 +478,13 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         const Batch &bt = batches[bi];
         const int64_t np = bt.p1 - bt.p0;
         const uint32_t tasks = (uint32_t)bt.tasks, base = (uint32_t)bt.base;
-        CK(cudaMemsetAsync(b_fctl.p, 0, 8, c->st));
+        CK(cudaMemsetAsync(b_fctl.p, 0, 16, c->st));
         if (tasks) {
-            CK(cudaMemsetAsync(b_ncand.p, 0, (size_t)tasks, c->st));
+            CK(cudaMemsetAsync(b_ncand.p, 0, (size_t)tasks + 1, c->st));
             CK(cudaMemsetAsync(b_slow.p, 0, (size_t)tasks, c->st));
             CK(cudaMemsetAsync(b_next.p, 0, 4, c->st));
             task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
-                                                                   tasks, b_desc.p);
+                                                                   tasks, b_desc.p, b_task_pair.p);
             CK(cudaGetLastError());
             // a persistent grid fed by the task counter
             const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
@@ -487,20 +514,31 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             c->launches += 4;
         }
         cudaEvent_t tf = mark();
-        // candidates per pair -> size the shared-memory finalize launch for the batch's largest ordinary pair, list the rest
-        pair_ncand_kernel<<<nblk((uint64_t)np, 128), 128, 0, c->st>>>(d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
-                                                                       b_ncand.p, b_pair_nc.p, b_fctl.p, b_big_list.p, b_big_nc.p);
+        // selection + ANI/AF: a warp per pair; the kernel lists the pairs it leaves to the CTA-per-pair kernels
+        if (tasks) {
+            exclusive_scan_u8(c, b_ncand.p, b_cand_off.p, (size_t)tasks + 1);  // b_ncand[tasks] = 0
+            cand_pack_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, prm, d_info_s.p + bt.p0, tasks, b_task_pair.p, b_ncand.p,
+                                                                  b_cand_off.p, b_cands.p, b_pcands.p);
+            CK(cudaGetLastError());
+            c->launches += 1;
+        }
+        finalize_warp_kernel<<<nblk((uint64_t)np, FW_WARPS), FW_WARPS * 32, fw_smem, c->st>>>(
+            view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_pcands.p, b_cand_off.p, d_perm.p + bt.p0, d_out,
+            fw_cap, b_fctl.p, b_mid_list.p, b_big_list.p, b_big_nc.p);
         CK(cudaGetLastError());
-        uint32_t fctl[2] = {0, 0};
-        CK(cudaMemcpyAsync(fctl, b_fctl.p, 8, cudaMemcpyDeviceToHost, c->st));
+        uint32_t fctl[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(fctl, b_fctl.p, 16, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        uint32_t fcap = 32;
-        while (fcap < fctl[0]) fcap <<= 1;
-        finalize_kernel<false><<<(unsigned)np, FIN_THREADS, FIN_BYTES_PER_CAND * (size_t)fcap, c->st>>>(
-            view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_cands.p, b_ncand.p, b_pair_nc.p,
-            d_perm.p + bt.p0, d_out, fcap, nullptr, nullptr, nullptr, nullptr);
-        CK(cudaGetLastError());
-        c->launches += 2;
+        c->launches += 1;
+        if (fctl[2]) {  // more than fw_cap candidates or more than FW_EDGES blocking relations: shared memory, one CTA per pair
+            uint32_t fcap = 32;
+            while (fcap < fctl[0]) fcap <<= 1;
+            finalize_kernel<false><<<fctl[2], FIN_THREADS, FIN_BYTES_PER_CAND * (size_t)fcap, c->st>>>(
+                view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np, b_pcands.p, b_cand_off.p,
+                d_perm.p + bt.p0, d_out, fcap, b_mid_list.p, nullptr, nullptr, nullptr);
+            CK(cudaGetLastError());
+            c->launches += 1;
+        }
         if (fctl[1]) {  // pairs beyond MAXP candidates: same kernel body on global scratch, one CTA per pair
             const uint32_t nbig = fctl[1];
             std::vector<uint32_t> h_nc(nbig), h_cap(nbig);
@@ -524,7 +562,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             d_big_off.upload(h_off, c->st);
             d_big_cap.upload(h_cap, c->st);
             finalize_kernel<true><<<nbig, FIN_THREADS, 0, c->st>>>(view, prm, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
-                                                                 b_cands.p, b_ncand.p, b_pair_nc.p, d_perm.p + bt.p0, d_out, 0,
+                                                                 b_pcands.p, b_cand_off.p, d_perm.p + bt.p0, d_out, 0,
                                                                  b_big_list.p, d_big_off.p, d_big_cap.p, d_big.p);
             CK(cudaGetLastError());
             c->launches++;
