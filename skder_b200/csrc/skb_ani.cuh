@@ -23,6 +23,8 @@
 //   end anchors left out), AF = span / genome length.  Pairs with more than MAXP candidates run the same code on
 //   global scratch (finalize_kernel<true>).
 #pragma once
+#include <type_traits>
+
 #include "skb_common.cuh"
 #include "skb_index.cuh"
 
@@ -192,9 +194,11 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
 //   D = R - q with R = rev ? -ref_pos : ref_pos: gap = |D_i - D_j|, d_ref = (D_i - D_j) + dq
 //   F = f + anchor_score (0 = empty slot: it can never beat `best`, which starts at anchor_score)
 // Colinear anchors (the usual case) chain onto one of the two nearest predecessors with a score no other one can
-// reach.  So only those two live in registers; the full 16-deep look-back window is a ring in shared memory
-// ([slot][thread]: conflict-free, slot = anchor index & 15), written once per anchor and read only on the two rare
-// paths: the full scan (the short cut could not prove the nearest two sufficient) and the bound rebuild.
+// reach.  So only those two live in registers (FR = F << 17 | root << 9 | cnt, the ring word, is carried packed: the
+// register a shared-memory store reads stays live for two more anchors, so the store never holds the next write to it
+// back -- ncu, round 2: those write-after-read waits and the MIO queue were 20 % of the kernel's stall samples with
+// three ring stores per anchor); the 16-deep look-back window is a ring of (D, FR) in shared memory, written once per
+// anchor and read only on the two rare paths: the bound rebuild and the full scan (which fetches Q from the anchors).
 //
 // Short cut.  Mx bounds what predecessors beyond the nearest two can offer: the largest F among those whose diagonal
 // lies within max_gap + DIAG_SLACK of Dref, where Dref follows this task's current diagonal to within DIAG_SLACK.
@@ -211,8 +215,9 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
 // rearrangement -- not a chance anchor), so the old chain's high scores neither keep the short cut off for the next
 // 16 anchors nor does one stray anchor derail it.  Stale entries that have left the window only make Mx too large
 // (a missed short cut).
-__global__ void __launch_bounds__(DP_THREADS, 6)
-chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uint16_t *__restrict__ task_n,
+template <bool WIDE>
+__global__ void __launch_bounds__(DP_THREADS, 8)
+chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_all, const uint16_t *__restrict__ task_n,
              uint32_t *__restrict__ res_all, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
              uint8_t *__restrict__ task_ncand, uint8_t *__restrict__ task_slow) {
     const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
@@ -220,16 +225,26 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
     if (w_n == 0) return;
     constexpr int UNR = DP_UNR;
-    static_assert(UNR % 2 == 0 && MAXA % UNR == 0 && LB % UNR == 0, "anchors are fetched 16 bytes at a time");
-    __shared__ int ringQ[LB][DP_THREADS], ringD[LB][DP_THREADS];
+    static_assert(UNR == 4 && MAXA % UNR == 0 && LB % UNR == 0, "anchors are fetched one 32-byte sector at a time");
+    // Diagonals of opposite strands are up to 2^32 apart.  When every padded position of the database is below
+    // 2^30 - 2^21 (any bacterial set) their differences fit an int and the diagonal tests are 32-bit (WIDE = false).
+    using diff_t = typename std::conditional<WIDE, long long, int>::type;
+    auto adiff = [](int a, int b) {
+        const diff_t d = (diff_t)a - (diff_t)b;
+        return d < 0 ? -d : d;
+    };
+    // The look-back window beyond the two nearest predecessors: diagonal and packed (F, root, cnt) per entry, a ring in
+    // shared memory ([slot][thread]: conflict-free, slot = anchor index & 15).  The query coordinate is not kept: the
+    // only path that wants it (the full scan, ~0.6 % of the steps) re-reads it from the anchor array.
+    __shared__ int ringD[LB][DP_THREADS];
     __shared__ uint32_t ringFR[LB][DP_THREADS];  // F << 17 | root << 9 | cnt  (0 = empty)
     __shared__ uint32_t tb_s[ENDS_K][DP_THREADS];  // dynamic indexing without local memory; column per thread
-    int *const rq = &ringQ[0][threadIdx.x], *const rd = &ringD[0][threadIdx.x];
+    int *const rd = &ringD[0][threadIdx.x];
     uint32_t *const rf = &ringFR[0][threadIdx.x];
 #pragma unroll
     for (int u = 0; u < LB; u++) rf[u * DP_THREADS] = 0;
-    int Q1 = 0, D1 = 0, F1 = 0, Q2 = 0, D2 = 0, F2 = 0;  // nearest, second nearest predecessor
-    uint32_t RC1 = 0, RC2 = 0;
+    int Q1 = 0, D1 = 0, Q2 = 0, D2 = 0;  // nearest, second nearest predecessor
+    uint32_t FR1 = 0, FR2 = 0;           // their ring words: (f + anchor_score) << 17 | root << 9 | cnt, 0 = none
     const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
     const uint64_t *ap = anc_all + (size_t)tt * MAXA;
     uint32_t *rp = res_all + (size_t)tt * MAXA;
@@ -262,20 +277,18 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
     int Mx = 0, Dref = 0;
     uint32_t off = 0;  // bit d: the d-th previous anchor (0 = nearest) is live and off Dref's diagonal
     const int diag_lim = prm.max_gap + DIAG_SLACK;
-    ulonglong2 vnext[UNR / 2];
-#pragma unroll
-    for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap) + x);
+    // four anchors = one 32-byte sector = one 256-bit load (the slabs are 2 KB apart: nothing to coalesce across lanes)
+    auto load4 = [&](int i, uint64_t (&v)[UNR]) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(ap + i));
+    };
+    uint64_t vnext[UNR];
+    load4(0, vnext);
     for (int i0 = 0; i0 < w_n; i0 += UNR) {
         uint64_t av[UNR];
 #pragma unroll
-        for (int x = 0; x < UNR / 2; x++) {
-            av[2 * x] = vnext[x].x;
-            av[2 * x + 1] = vnext[x].y;
-        }
-        if (i0 + UNR < MAXA) {  // next iteration's anchors
-#pragma unroll
-            for (int x = 0; x < UNR / 2; x++) vnext[x] = __ldcg(reinterpret_cast<const ulonglong2 *>(ap + i0 + UNR) + x);
-        }
+        for (int x = 0; x < UNR; x++) av[x] = vnext[x];
+        if (i0 + UNR < MAXA) load4(i0 + UNR, vnext);  // next iteration's anchors
         const int ring0 = (i0 & (LB - 1)) * DP_THREADS;  // slot of anchor i0; anchor i0 + x sits x slots further
         uint32_t outp[UNR];
 #pragma unroll
@@ -289,26 +302,24 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
             int best = prm.anchor_score;
             uint32_t brc = (uint32_t)i << 9;  // own root, cnt 0 (+1 below)
             const bool live = i < my_n;
-            auto relax = [&](int Qj, int Dj, int Fj, uint32_t RCj) {
+            auto relax = [&](int Qj, int Dj, uint32_t FRj) {
                 const int dq1 = qi - Qj;  // dq - 1
                 const int dd = Di - Dj;
                 const int dr1 = dd + dq1;  // d_ref - 1
                 const int gap = dd < 0 ? -dd : dd;
-                const int cand = Fj - gap;
+                const int cand = (int)(FRj >> 17) - gap;
                 if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > best) {
                     best = cand;
-                    brc = RCj;
+                    brc = FRj & 0x1ffffu;
                 }
             };
-            relax(Q1, D1, F1, RC1);  // the nearest predecessor: ties keep it
-            relax(Q2, D2, F2, RC2);
-            long long dj = (long long)Di - Dref;  // 64-bit: opposite strands are up to 2^32 apart
-            dj = dj < 0 ? -dj : dj;
+            relax(Q1, D1, FR1);  // the nearest predecessor: ties keep it
+            relax(Q2, D2, FR2);
+            const diff_t dj = adiff(Di, Dref);
             bool jump = live && dj > DIAG_SLACK;
             bool settled = !live || Mx <= best;
             if (__any_sync(0xffffffffu, jump)) {
-                long long dp = (long long)Di - D1;
-                dp = dp < 0 ? -dp : dp;
+                const diff_t dp = adiff(Di, D1);
                 const bool quick = (off >> 2) == 0 && dj > diag_lim + DIAG_SLACK;
                 int m2 = 0;
                 uint32_t offn = 0;  // `off` relative to this anchor's diagonal, entries beyond the nearest two
@@ -317,8 +328,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                     for (int d = 2; d < LB; d++) {
                         const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
                         const uint32_t fr = rf[sl];
-                        long long dd = (long long)rd[sl] - Di;
-                        dd = dd < 0 ? -dd : dd;
+                        const diff_t dd = adiff(rd[sl], Di);
                         if (dd <= diag_lim) m2 = max(m2, (int)(fr >> 17));
                         if (fr && dd > DIAG_SLACK) offn |= 1u << d;
                     }
@@ -329,26 +339,25 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                         Mx = m2;
                         Dref = Di;
                         if (quick) offn = 0xfffcu & ((1u << (i < LB ? i : LB)) - 1u);  // all the old diagonal's entries
-                        long long d2 = (long long)D2 - Di;
-                        d2 = d2 < 0 ? -d2 : d2;
-                        off = offn | ((F2 != 0 && d2 > DIAG_SLACK) ? 2u : 0u);
+                        off = offn | ((FR2 != 0 && adiff(D2, Di) > DIAG_SLACK) ? 2u : 0u);
                         jump = false;
                     }
                 }
             }
             if (!__all_sync(0xffffffffu, settled)) {
+                if (!settled) {
 #pragma unroll 1
-                for (int d = 2; d < LB; d++) {
-                    const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
-                    const uint32_t fr = rf[sl];
-                    relax(rq[sl], rd[sl], (int)(fr >> 17), fr & 0x1ffffu);
+                    for (int d = 2; d < LB; d++) {
+                        const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
+                        const uint32_t fr = rf[sl];
+                        if (fr == 0) continue;  // empty slot (also: before the chunk's first anchor)
+                        const uint32_t lo = __ldcg(reinterpret_cast<const uint32_t *>(ap + (i - 1 - d)));
+                        relax((int)((lo >> 17) & 0x7fffu) + (int)(((lo >> 16) & 1u) << 20) + 1, rd[sl], fr);
+                    }
                 }
             }
-            {  // the second nearest predecessor is beyond the nearest two of the next anchor
-                int dd = D2 - Dref;
-                dd = dd < 0 ? -dd : dd;
-                Mx = max(Mx, dd <= diag_lim ? F2 : 0);
-            }
+            // the second nearest predecessor is beyond the nearest two of the next anchor
+            Mx = max(Mx, adiff(D2, Dref) <= diag_lim ? (int)(FR2 >> 17) : 0);
             const uint32_t rci = brc + 1;
             outp[x] = ((uint32_t)best << 17) | rci;
             if (live && best >= prm.min_score && (int)(rci & 0x1ffu) >= prm.min_anchors) {
@@ -362,18 +371,13 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *anc_all, const uin
                     cur_e = e;
                 }
             }
-            Q2 = Q1, D2 = D1, F2 = F1, RC2 = RC1;
-            Q1 = qi + 1, D1 = Di, F1 = live ? best + prm.anchor_score : 0, RC1 = rci;
-            rq[ring0 + x * DP_THREADS] = Q1;
+            Q2 = Q1, D2 = D1, FR2 = FR1;
+            Q1 = qi + 1, D1 = Di, FR1 = live ? outp[x] + ((uint32_t)prm.anchor_score << 17) : 0u;
             rd[ring0 + x * DP_THREADS] = D1;
-            rf[ring0 + x * DP_THREADS] = live ? outp[x] + ((uint32_t)prm.anchor_score << 17) : 0u;
+            rf[ring0 + x * DP_THREADS] = FR1;
             off = ((off << 1) | (jump ? 1u : 0u)) & 0xffffu;
         }
-        if (i0 < my_n) {
-#pragma unroll
-            for (int x = 0; x < UNR / 2; x++)
-                __stcg(reinterpret_cast<uint2 *>(rp + i0) + x, make_uint2(outp[2 * x], outp[2 * x + 1]));
-        }
+        if (i0 < my_n) __stcg(reinterpret_cast<uint4 *>(rp + i0), make_uint4(outp[0], outp[1], outp[2], outp[3]));
     }
     // ---- the chunk's top candidates, by (score desc, q0, r0), into the task's slots
     if (my_n == 0) return;

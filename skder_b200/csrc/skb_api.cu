@@ -461,6 +461,15 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     b_mid_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_nc.reserve((size_t)cap_pairs, 0, c->st);
+    // chain_kernel compares diagonals (reference position -/+ query position, sign by strand) in 32 bits when no padded
+    // position of the database comes near 2^30; SKB_WIDE_DIAG=1 forces the 64-bit variant (tests run both)
+    bool wide_diag = std::getenv("SKB_WIDE_DIAG") != nullptr && atoi(std::getenv("SKB_WIDE_DIAG")) != 0;
+    for (int32_t g = 0; g < c->n_indexed && !wide_diag; g++) {
+        const uint32_t k1 = c->h_ctg_off[(size_t)g + 1];
+        if (k1 > c->h_ctg_off[(size_t)g] &&
+            (uint64_t)c->h_ctg_pstart[k1 - 1] + c->h_ctg_len[k1 - 1] >= (1ull << 30) - (1ull << 21))
+            wide_diag = true;
+    }
     static const bool trace = std::getenv("SKB_TRACE") != nullptr;  // diagnosis: per-kernel timeline on stderr
     struct Span { const char *name; size_t batch; cudaEvent_t e0, e1; };
     std::vector<Span> spans;
@@ -503,8 +512,12 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st));
             c->anchor_ev_used += 2;
             t0 = mark();
-            chain_kernel<<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_tn.p, b_res.p, b_desc.p,
-                                                                            b_cands.p, b_ncand.p, b_slow.p);
+            if (wide_diag)
+                chain_kernel<true><<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_tn.p, b_res.p, b_desc.p,
+                                                                                      b_cands.p, b_ncand.p, b_slow.p);
+            else
+                chain_kernel<false><<<nblk(tasks, DP_THREADS), DP_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_tn.p, b_res.p, b_desc.p,
+                                                                                       b_cands.p, b_ncand.p, b_slow.p);
             CK(cudaGetLastError());
             if (trace) spans.push_back({"chain", bi, t0, mark()});
             const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
