@@ -320,17 +320,21 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
             bool settled = !live || Mx <= best;
             if (__any_sync(0xffffffffu, jump)) {
                 const diff_t dp = adiff(Di, D1);
-                const bool quick = (off >> 2) == 0 && dj > diag_lim + DIAG_SLACK;
+                // A far jump leaves every entry on Dref's diagonal (`off` bit clear: within DIAG_SLACK of Dref) out of
+                // its reach and off its own diagonal, without looking; only the entries flagged in `off` are read.
+                const bool far = dj > diag_lim + DIAG_SLACK;
+                const bool quick = far && (off >> 2) == 0;
+                const uint32_t window = 0xfffcu & ((1u << (i < LB ? i : LB)) - 1u);  // anchors i-3 .. i-16 that exist (all live)
                 int m2 = 0;
-                uint32_t offn = 0;  // `off` relative to this anchor's diagonal, entries beyond the nearest two
+                uint32_t offn = far ? window & ~off : 0u;  // `off` relative to this anchor's diagonal, beyond the nearest two
                 if (__any_sync(0xffffffffu, jump && !quick)) {
 #pragma unroll 1
-                    for (int d = 2; d < LB; d++) {
+                    for (uint32_t todo = (jump && !quick) ? (far ? window & off : window) : 0u; todo; todo &= todo - 1) {
+                        const int d = __ffs((int)todo) - 1;
                         const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
-                        const uint32_t fr = rf[sl];
                         const diff_t dd = adiff(rd[sl], Di);
-                        if (dd <= diag_lim) m2 = max(m2, (int)(fr >> 17));
-                        if (fr && dd > DIAG_SLACK) offn |= 1u << d;
+                        if (dd <= diag_lim) m2 = max(m2, (int)(rf[sl] >> 17));
+                        if (dd > DIAG_SLACK) offn |= 1u << d;
                     }
                 }
                 if (jump) {
@@ -338,7 +342,6 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
                     if (dp <= DIAG_SLACK) {  // the previous anchor is on this diagonal too: follow it
                         Mx = m2;
                         Dref = Di;
-                        if (quick) offn = 0xfffcu & ((1u << (i < LB ? i : LB)) - 1u);  // all the old diagonal's entries
                         off = offn | ((FR2 != 0 && adiff(D2, Di) > DIAG_SLACK) ? 2u : 0u);
                         jump = false;
                     }
