@@ -146,45 +146,85 @@ __global__ void task_setup_kernel(DbView db, const PairInfo *__restrict__ info, 
 
 // ---- K4a: anchors.  One warp per task; the only dependent reads are descriptor -> seed records ->
 // buckets, covered by the other resident warps.
+// 3 CTAs of 8 warps per SM = 80 registers per thread: at 4 (64 registers) the four buckets in flight per lane spill,
+// and local-memory traffic competes for the very L1 data pipe the scattered bucket reads are bound by (round 2 A/B on
+// config3: 5.0 ms per launch at 3 CTAs without spills, 6.8 ms at 4 CTAs with 124 bytes of spill stores).
 #ifndef SKB_ANC_MIN_CTAS
-#define SKB_ANC_MIN_CTAS 4
+#define SKB_ANC_MIN_CTAS 3
 #endif
+#ifndef SKB_ANC_GRAB
+#define SKB_ANC_GRAB 8
+#endif
+constexpr int ANC_GRAB = SKB_ANC_GRAB;  // consecutive tasks a warp takes from the counter at a time (<= 32)
+
+template <bool NARROW>
 __global__ void __launch_bounds__(ANC_THREADS, SKB_ANC_MIN_CTAS)
 anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint32_t n_tasks,
               uint64_t *__restrict__ anc_all, uint16_t *__restrict__ task_n, uint32_t *__restrict__ next_task) {
     __shared__ uint32_t stage_all[ANC_THREADS / 32][32 * STAGE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stage = stage_all[warp];
+    __shared__ TaskDesc sdesc_all[ANC_THREADS / 32][ANC_GRAB];
+    TaskDesc *sdesc = sdesc_all[warp];
+    using seed_t = typename std::conditional<NARROW, uint2, uint64_t>::type;
     // Tasks are handed out in order from one counter, not strided by CTA: the grid is persistent and, next to the
     // consumer kernels of the previous batch, its CTAs become resident at different times; a CTA that starts late
     // must join the others on the reference tables that are in L2 NOW (tasks are reference-major), not work
     // through a fixed share milliseconds behind them (measured: 11 ms -> 54 ms per launch with a strided loop).
+    // A warp takes ANC_GRAB consecutive tasks per visit to the counter: counter -> descriptor -> seed records ->
+    // buckets is a chain of four dependent round trips of ~1 us each against ~0.4 us of instructions per task (ncu,
+    // round 2: 41 % of the stall samples on the long scoreboard at 67 % issue).  With a grab the first two are paid
+    // once per ANC_GRAB tasks (the descriptors wait in shared memory), and the first seed records of the next task
+    // are fetched while the current task's last buckets are in flight (emit_anchors' qs_next).
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(next_task, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tasks) break;
-        const TaskDesc d = desc[t];
-        const int nseeds = (int)d.nseeds;
-        int n = 0;
-        if (nseeds > 0) {
-            const uint64_t *qs = db.seeds + d.seed_idx;
-            const uint64_t *T = db.tab + d.tab_idx;
-            uint64_t *anc = anc_all + (size_t)t * MAXA;
-            uint64_t sdn[PJ];
-            // optimistic pass with the full multiplicity cap; if the chunk overflows MAXA, halve the cap
-            // until it fits (oracle rule; rare)
-            int mult = prm.max_mult;
-            for (;;) {
-                load_first_batch(qs, nseeds, lane, sdn);
-                n = emit_anchors(qs, nseeds, d.cstart, T, d.nb, mult, prm.max_mult, MAXA, stage, anc, lane, sdn, qs, 0);
-                if (n <= MAXA || mult == 1) break;
-                mult >>= 1;
-            }
-            if (n > MAXA || n < prm.min_anchors) n = 0;
-        }
-        if (lane == 0) task_n[t] = (uint16_t)n;
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(next_task, (uint32_t)ANC_GRAB);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 >= n_tasks) break;
+        const int nt = (int)min((uint32_t)ANC_GRAB, n_tasks - t0);
+        __syncwarp();  // the previous grab's descriptors are no longer read
+        if (lane < nt) sdesc[lane] = desc[t0 + lane];
         __syncwarp();
+        auto first_batch = [&](const seed_t *q, int ns, seed_t (&sdn)[PJ]) {
+            if constexpr (NARROW)
+                load_first_batch_narrow(q, ns, lane, sdn);
+            else
+                load_first_batch(q, ns, lane, sdn);
+        };
+        seed_t sdn[PJ];
+        first_batch(reinterpret_cast<const seed_t *>(db.seeds + sdesc[0].seed_idx), (int)sdesc[0].nseeds, sdn);
+        for (int k = 0; k < nt; k++) {
+            // descriptor fields come from shared memory (broadcast reads) where they are used: nothing is held in
+            // registers across the grab
+            const TaskDesc &d = sdesc[k];
+            const int kn = k + 1 < nt ? k + 1 : k;
+            const int nseeds = (int)d.nseeds, ns_next = k + 1 < nt ? (int)sdesc[kn].nseeds : 0;
+            const seed_t *qs = reinterpret_cast<const seed_t *>(db.seeds + d.seed_idx);
+            const seed_t *qs_next = reinterpret_cast<const seed_t *>(db.seeds + sdesc[kn].seed_idx);
+            int n = 0;
+            if (nseeds > 0) {
+                const uint64_t *T = db.tab + d.tab_idx;
+                uint64_t *anc = anc_all + (size_t)(t0 + k) * MAXA;
+                // optimistic pass with the full multiplicity cap; if the chunk overflows MAXA, halve the cap
+                // until it fits (oracle rule; rare)
+                int mult = prm.max_mult;
+                for (;;) {
+                    if constexpr (NARROW)
+                        n = emit_anchors_narrow(qs, nseeds, d.cstart, T, d.nb, mult, prm.max_mult, MAXA, stage, anc, lane, sdn,
+                                                qs_next, ns_next);
+                    else
+                        n = emit_anchors(qs, nseeds, d.cstart, T, d.nb, mult, prm.max_mult, MAXA, stage, anc, lane, sdn, qs_next,
+                                         ns_next);
+                    if (n <= MAXA || mult == 1) break;
+                    mult >>= 1;
+                    first_batch(qs, nseeds, sdn);
+                }
+                if (n > MAXA || n < prm.min_anchors) n = 0;
+            } else
+                first_batch(qs_next, ns_next, sdn);
+            if (lane == 0) task_n[t0 + k] = (uint16_t)n;
+            __syncwarp();
+        }
     }
 }
 

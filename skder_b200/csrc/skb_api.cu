@@ -461,8 +461,9 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     b_mid_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_list.reserve((size_t)cap_pairs, 0, c->st);
     b_big_nc.reserve((size_t)cap_pairs, 0, c->st);
-    // chain_kernel compares diagonals (reference position -/+ query position, sign by strand) in 32 bits when no padded
-    // position of the database comes near 2^30; SKB_WIDE_DIAG=1 forces the 64-bit variant (tests run both)
+    // When no padded position of the database comes near 2^30, anchor_kernel matches and decodes seed records by their
+    // 32-bit halves and chain_kernel compares diagonals (reference position -/+ query position, sign by strand) in 32
+    // bits; SKB_WIDE_DIAG=1 forces the general variants (tests run both)
     bool wide_diag = std::getenv("SKB_WIDE_DIAG") != nullptr && atoi(std::getenv("SKB_WIDE_DIAG")) != 0;
     for (int32_t g = 0; g < c->n_indexed && !wide_diag; g++) {
         const uint32_t k1 = c->h_ctg_off[(size_t)g + 1];
@@ -496,7 +497,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                                                                    tasks, b_desc.p, b_task_pair.p);
             CK(cudaGetLastError());
             // a persistent grid fed by the task counter
-            const unsigned g1 = std::min<unsigned>(nblk(tasks, ANC_THREADS / 32), (unsigned)c->sm_count * 32u);
+            const unsigned g1 = std::min<unsigned>(nblk(tasks, (ANC_THREADS / 32) * ANC_GRAB), (unsigned)c->sm_count * 32u);
             if ((int)c->anchor_ev.size() < c->anchor_ev_used + 2) {
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0));
@@ -506,7 +507,10 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
             }
             CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used], c->st));
             cudaEvent_t t0 = mark();
-            anchor_kernel<<<g1, ANC_THREADS, 0, c->st>>>(view, prm, b_desc.p, tasks, b_anc.p, b_tn.p, b_next.p);
+            if (wide_diag)
+                anchor_kernel<false><<<g1, ANC_THREADS, 0, c->st>>>(view, prm, b_desc.p, tasks, b_anc.p, b_tn.p, b_next.p);
+            else
+                anchor_kernel<true><<<g1, ANC_THREADS, 0, c->st>>>(view, prm, b_desc.p, tasks, b_anc.p, b_tn.p, b_next.p);
             CK(cudaGetLastError());
             if (trace) spans.push_back({"anchor", bi, t0, mark()});
             CK(cudaEventRecord(c->anchor_ev[c->anchor_ev_used + 1], c->st));
