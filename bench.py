@@ -70,24 +70,63 @@ def workload_name(w):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled during the timed region: NVML from a thread of this process (pynvml), or an
+    `nvidia-smi -lms` child where NVML is not importable.  NVML in-process keeps the polling light: every query takes
+    a driver-wide lock, and an nvidia-smi loop per rank was seen to stall cudaMemGetInfo / cudaMalloc of the timed
+    steps by tens of milliseconds."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD = 0.25
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.th, self.stop = index, [], None, None, threading.Event()
+        self.sm, self.mx, self.reasons = [], [], set()
 
     def __enter__(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+
+            def poll():
+                while True:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.reasons.update(n for n, b in bits.items() if r & b)
+                    except pynvml.NVMLError:
+                        pass
+                    if self.stop.wait(self.PERIOD):
+                        return
+
+            self.th = threading.Thread(target=poll, daemon=True)
+            self.th.start()
+            return self
+        except Exception:
+            self.th = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
+                ["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
         return self
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip()]
+        if ids and self.index < len(ids) and ids[self.index].strip().isdigit():
+            return int(ids[self.index])
+        return self.index
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -98,8 +137,15 @@ class ClockSampler:
             time.sleep(0.15)
             self.proc.terminate()
             self.th.join(timeout=2)
+        elif self.th:
+            self.stop.set()
+            self.th.join(timeout=2)
 
     def summary(self):
+        if self.proc is None and self.sm:
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": [n for n in names if n in self.reasons], "samples": len(self.sm), "source": "nvml"}
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
@@ -107,7 +153,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -412,6 +458,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: bench.py has no CPU path for --impl ours")
     torch.cuda.set_device(local)
+    numa_cpus = multi.bind_to_gpu_numa_node(torch, local) if world > 1 and os.environ.get("SKB_NO_NUMA_BIND") != "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.workload in SEARCH_WORKLOADS:
@@ -569,6 +616,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (sketch DB %.1f GB per rank)" % (
                        (st.sum_query_seeds and (n_full * L / 125 * 8 * 3) / 1e9) or 0.0),
                    "ms_screen": float(np.mean(ms_screen)), "ms_ani": ani_ms, "gen_s": t_gen,
+                   "host_cpus_rank0": ("%d CPUs local to the GPU" % len(numa_cpus)) if numa_cpus else "unbound",
                    "wall_ms_per_step": t_wall / args.steps * 1e3,
                    # `value` starts from the indexed sketch DB ("sketches resident on device"); the index
                    # build (seed tables + inverted marker index) is the prescreen's set-up and is reported here

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <cub/cub.cuh>
 #include <map>
 #include <string>
@@ -122,6 +123,8 @@ struct skb_ctx {
     int kept_x2 = 0;
     int tab_x2 = 4;        // seed-table buckets per seed, times two: 4 / 2 / 1 = 0.5 / 1 / 2 records per 4-slot bucket
     int tab_x2_forced = 0; // SKB_TAB_X2 (tests exercise the overflow chain with 1)
+    int x2_decided = 0;    // density chosen from the free device memory the last time it was asked for ...
+    uint64_t x2_decided_seeds = 0;  // ... and the owned seed count it was chosen for
     DevBuf<uint64_t> d_seed_off, d_tab, d_tab_off, d_total_len, d_inv, d_markers, d_marker_off;
     DevBuf<uint32_t> d_tab_buckets;
     DevBuf<uint32_t> d_chunk_begin, d_chunk_start, d_chunk_len, d_chunk_off, d_ctg_pstart, d_ctg_len, d_ctg_off,
@@ -410,12 +413,14 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     // Batches of pairs bound the scratch (<= 8 Mi tasks per batch) and keep a batch's reference tables and
     // candidates warm in L2 between its kernels.  One in-order stream: running the anchor kernel of batch b+1 beside
     // chain/finalize of batch b on a second stream was measured slower in every configuration (round 1).
-    static const uint64_t want_batches = [] {
-        const char *e = std::getenv("SKB_PAIR_BATCHES");
-        return (uint64_t)(e ? std::max(1, atoi(e)) : 6);
+    // About 5 Mi tasks per batch (SKB_PAIR_BATCH_TASKS): six batches for config3 on one GPU (measured best there), one
+    // for an eighth of it -- every batch costs ~0.3 ms of launches, scans and one host round trip.
+    static const uint64_t batch_tasks = [] {
+        const char *e = std::getenv("SKB_PAIR_BATCH_TASKS");
+        return (uint64_t)(e ? std::max(1 << 16, atoi(e)) : (5 << 20));
     }();
-    const uint64_t max_tasks =
-        std::min<uint64_t>(8ull << 20, std::max<uint64_t>(1ull << 18, (total_tasks + want_batches - 1) / want_batches));
+    const uint64_t want_batches = std::max<uint64_t>(1, (total_tasks + batch_tasks / 2) / batch_tasks);
+    const uint64_t max_tasks = std::min<uint64_t>(8ull << 20, (total_tasks + want_batches - 1) / want_batches + 4096);
     struct Batch { int64_t p0, p1; uint64_t base, tasks; };
     std::vector<Batch> batches;
     {
@@ -927,6 +932,18 @@ int skb_add_genomes(skb_ctx *ctx, int32_t n, const skb_packed *const *genomes) {
 
 static int index_impl(skb_ctx *c, bool tables_only) {
     {
+        static const bool trace = std::getenv("SKB_TRACE") != nullptr;  // diagnosis: phase times on stderr (adds syncs)
+        double t_last = 0;
+        auto lap = [&](const char *what) {
+            if (!trace) return;
+            cudaStreamSynchronize(c->st);
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+            if (what) fprintf(stderr, "[skb trace] index %-14s %7.2f ms\n", what, now - t_last);
+            t_last = now;
+        };
+        lap(nullptr);
         const int32_t n = c->n();
         if (n == 0) return fail(c, SKB_ESTATE, "no genomes added");
         const uint64_t n_seeds = c->h_seed_off.back();
@@ -944,7 +961,10 @@ static int index_impl(skb_ctx *c, bool tables_only) {
         // the sparsest seed tables the device holds comfortably: a lookup is one sector read unless its bucket
         // overflowed, and at 0.5 records per bucket that is rare enough not to stall a warp (skb_probe.cuh)
         c->tab_x2 = reuse ? c->kept_x2 : c->tab_x2_forced;
+        if (!c->tab_x2 && c->x2_decided && c->x2_decided_seeds == own_seeds_now) c->tab_x2 = c->x2_decided;
         if (!c->tab_x2) {
+            // decided once per sketch-DB size: cudaMemGetInfo takes a driver-wide lock and stalls for tens of ms
+            // whenever a monitoring tool (nvidia-smi / NVML polling) holds it -- seen as 20-80 ms spikes of this call
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             const double budget = std::min(0.35 * (double)total_b,
@@ -958,6 +978,8 @@ static int index_impl(skb_ctx *c, bool tables_only) {
                     c->tab_x2 = x2;
                     break;
                 }
+            c->x2_decided = c->tab_x2;
+            c->x2_decided_seeds = own_seeds_now;
         }
         tab_off.assign(n + 1, 0);
         tab_buckets.assign(n, 0);
@@ -983,6 +1005,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
             }
             c->h_chunk_off[g + 1] = (uint32_t)chunk_start.size();
         }
+        lap("host tables");
         c->d_seed_off.upload(c->h_seed_off, c->st);
         c->d_tab_off.upload(tab_off, c->st);
         c->d_tab_buckets.upload(tab_buckets, c->st);
@@ -993,6 +1016,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
         c->d_chunk_start.upload(chunk_start, c->st);
         c->d_chunk_len.upload(chunk_len, c->st);
         c->d_chunk_off.upload(c->h_chunk_off, c->st);
+        lap("uploads");
         // ---- K2: seed hash indices + repeat flags + chunk_begin
         c->d_tab.reserve(tab_off[n] + BUCKET, reuse ? tab_off[n] : 0, c->st);
         if (!reuse) {
@@ -1012,6 +1036,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
                 c->launches += 3;
             }
         }
+        lap("seed tables");
         c->kept_n = 0;
         if (tables_only) {  // the caller exchanges sketches next (skb_clear_keep_tables): nothing else is needed yet
             CK(cudaStreamSynchronize(c->st));
@@ -1027,6 +1052,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
                                                                    c->d_chunk_start.p, c->d_chunk_begin.p, n_entries, 0);
         CK(cudaGetLastError());
         c->launches++;
+        lap("chunk_begin");
         // ---- markers: sort raw keys, unique -> inverted index; per-genome counts; per-genome lists
         c->d_marker_cnt.reserve((size_t)n, 0, c->st);
         CK(cudaMemsetAsync(c->d_marker_cnt.p, 0, (size_t)n * 4, c->st));
@@ -1053,6 +1079,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
                                                                            c->d_inv.p, c->d_marker_cnt.p);
             CK(cudaGetLastError());
             c->launches += 3;
+            lap("inverted index");
             // per-genome sorted lists: swap key halves, sort again, strip ids
             c->d_markers.reserve(nu + 1, 0, c->st);
             swap_key_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_inv.p, nu, d_sorted.p);
@@ -1068,6 +1095,7 @@ static int index_impl(skb_ctx *c, bool tables_only) {
         }
         c->d_marker_off.upload(c->h_marker_off, c->st);
         CK(cudaStreamSynchronize(c->st));
+        lap("marker lists");
         c->n_indexed = n;
         c->n_inv_genomes = n;
         c->n_mkeys_indexed = c->n_mkeys;

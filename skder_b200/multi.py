@@ -253,3 +253,43 @@ def partition_rows(n, part, n_parts):
     m = a % (2 * n_parts)
     rows = a[np.where(m < n_parts, m, 2 * n_parts - 1 - m) == part]
     return rows, int((n - 1 - rows).sum())
+
+
+def bind_to_gpu_numa_node(torch, device_index):
+    """Pin this process (and so its first-touch page placement) to the CPUs local to its GPU's PCIe root before any
+    pinned staging buffer is allocated.  With one process per GPU and no binding, the pinned buffers of all ranks tend
+    to land on whichever socket the launcher ran on and every upload of the far GPUs crosses the socket interconnect:
+    eight simultaneous uploads then share ~170 GB/s instead of running at ~50 GB/s each.  Returns the CPU list used,
+    or None where sysfs does not say (single-socket boxes, containers without /sys/bus/pci)."""
+    import os
+
+    try:
+        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        if not bdf:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+            phys = int(vis[device_index]) if vis and vis[device_index].strip().isdigit() else device_index
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:  # NVML prints a 32-bit domain, sysfs a 16-bit one
+            bdf = bdf[4:]
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
