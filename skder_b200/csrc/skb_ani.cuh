@@ -37,7 +37,7 @@ constexpr int NEG_F = -(1 << 24);             // DP score of an empty window slo
 constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA pass
 constexpr int DP_THREADS = 128;               // K4b: one task per thread
 constexpr int END_THREADS = 256;              // K4c: 8 warps = 8 tasks per CTA pass
-constexpr int MAXA = 256;                     // anchors per chunk
+constexpr int MAXA = SLAB;                    // anchors per chunk (256)
 constexpr int MAXP = 4096;                    // chain candidates per pair the shared-memory finalize kernel takes
 constexpr int STAGE = 8;                      // max_mult upper bound (hits staged per seed)
 constexpr int ENDS_K = 8;                     // qualifying DP trees per chunk tracked inside chain_kernel
@@ -204,7 +204,7 @@ anchor_kernel(DbView db, AniParams prm, const TaskDesc *__restrict__ desc, uint3
             int n = 0;
             if (nseeds > 0) {
                 const uint64_t *T = db.tab + d.tab_idx;
-                uint64_t *anc = anc_all + (size_t)(t0 + k) * MAXA;
+                uint64_t *anc = anc_all + slab_base(t0 + k);  // entry i of the task at anc[slab_off(i)]
                 // optimistic pass with the full multiplicity cap; if the chunk overflows MAXA, halve the cap
                 // until it fits (oracle rule; rare)
                 int mult = prm.max_mult;
@@ -259,7 +259,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(DP_THREADS, 8)
 chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_all, const uint16_t *__restrict__ task_n,
              uint32_t *__restrict__ res_all, const TaskDesc *__restrict__ desc, Cand *__restrict__ cands,
-             uint8_t *__restrict__ task_ncand, uint8_t *__restrict__ task_slow) {
+             uint8_t *__restrict__ task_ncand, uint32_t *__restrict__ slow_list /* [0] count, then task ids */) {
     const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
     const int my_n = t < n_tasks ? (int)task_n[t] : 0;
     const int w_n = (int)__reduce_max_sync(0xffffffffu, (unsigned)my_n);
@@ -286,8 +286,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
     int Q1 = 0, D1 = 0, Q2 = 0, D2 = 0;  // nearest, second nearest predecessor
     uint32_t FR1 = 0, FR2 = 0;           // their ring words: (f + anchor_score) << 17 | root << 9 | cnt, 0 = none
     const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
-    const uint64_t *ap = anc_all + (size_t)tt * MAXA;
-    uint32_t *rp = res_all + (size_t)tt * MAXA;
+    const uint64_t *ap = anc_all + slab_base(tt);  // entry i at ap[slab_off(i)]
+    uint32_t *rp = res_all + slab_base(tt);
     const unsigned band = (unsigned)prm.band_bp;
     // chain ends, tracked on the fly: per DP tree (root) the best qualifying end as
     //   (f << 16) | (255 - i) << 8 | root   -- max over a tree = highest score, ties lowest index.
@@ -320,7 +320,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
     // four anchors = one 32-byte sector = one 256-bit load (the slabs are 2 KB apart: nothing to coalesce across lanes)
     auto load4 = [&](int i, uint64_t (&v)[UNR]) {
         asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(ap + i));
+                     : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(ap + slab_off((uint32_t)i)));
     };
     uint64_t vnext[UNR];
     load4(0, vnext);
@@ -394,7 +394,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
                         const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
                         const uint32_t fr = rf[sl];
                         if (fr == 0) continue;  // empty slot (also: before the chunk's first anchor)
-                        const uint32_t lo = __ldcg(reinterpret_cast<const uint32_t *>(ap + (i - 1 - d)));
+                        const uint32_t lo = __ldcg(reinterpret_cast<const uint32_t *>(ap + slab_off((uint32_t)(i - 1 - d))));
                         relax((int)((lo >> 17) & 0x7fffu) + (int)(((lo >> 16) & 1u) << 20) + 1, rd[sl], fr);
                     }
                 }
@@ -420,13 +420,13 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
             rf[ring0 + x * DP_THREADS] = FR1;
             off = ((off << 1) | (jump ? 1u : 0u)) & 0xffffu;
         }
-        if (i0 < my_n) __stcg(reinterpret_cast<uint4 *>(rp + i0), make_uint4(outp[0], outp[1], outp[2], outp[3]));
+        if (i0 < my_n) __stcg(reinterpret_cast<uint4 *>(rp + slab_off((uint32_t)i0)), make_uint4(outp[0], outp[1], outp[2], outp[3]));
     }
     // ---- the chunk's top candidates, by (score desc, q0, r0), into the task's slots
     if (my_n == 0) return;
     flush(cur_e);
     if (slow) {
-        task_slow[t] = 1;
+        slow_list[1 + atomicAdd(&slow_list[0], 1u)] = t;
         return;
     }
     uint64_t key[ENDS_K];
@@ -436,8 +436,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
         key[k] = ~0ull;
         const uint32_t e = tb[k * DP_THREADS];
         if (e) {
-            const uint64_t ar = __ldcg(ap + (e & 0xffu));
-            const uint64_t ae = __ldcg(ap + (MAXA - 1 - ((e >> 8) & 0xffu)));
+            const uint64_t ar = __ldcg(ap + slab_off(e & 0xffu));
+            const uint64_t ae = __ldcg(ap + slab_off(MAXA - 1 - ((e >> 8) & 0xffu)));
             const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
             key[k] = ((uint64_t)(8191u - (e >> 16)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
             m++;
@@ -459,8 +459,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
             if (k == bk) key[k] = ~0ull;
         const uint32_t e = tb[bk * DP_THREADS];
         const int iend = MAXA - 1 - (int)((e >> 8) & 0xffu);
-        const uint64_t ar = __ldcg(ap + (e & 0xffu)), ae = __ldcg(ap + iend);
-        const uint32_t x = __ldcg(rp + iend);  // written above by this thread
+        const uint64_t ar = __ldcg(ap + slab_off(e & 0xffu)), ae = __ldcg(ap + slab_off((uint32_t)iend));
+        const uint32_t x = __ldcg(rp + slab_off((uint32_t)iend));  // written above by this thread
         Cand c;
         c.q0 = d.cstart + an_q(ar);
         c.q1 = d.cstart + an_q(ae);
@@ -483,25 +483,26 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
 // fixed candidate slots.
 __global__ void __launch_bounds__(END_THREADS)
 ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_all, const uint32_t *__restrict__ res_all,
-            const uint16_t *__restrict__ task_n, const TaskDesc *__restrict__ desc, const uint8_t *__restrict__ task_slow,
+            const uint16_t *__restrict__ task_n, const TaskDesc *__restrict__ desc, const uint32_t *__restrict__ slow_list,
             Cand *__restrict__ cands, uint8_t *__restrict__ task_ncand) {
     __shared__ uint32_t bor_all[END_THREADS / 32][MAXA];
     __shared__ __align__(16) uint32_t lst_all[END_THREADS / 32][SLOTS * 8 + SLOTS * 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *bor = bor_all[warp];
     const uint32_t warps_total = gridDim.x * (END_THREADS / 32);
-    for (uint32_t t = blockIdx.x * (END_THREADS / 32) + warp; t < n_tasks; t += warps_total) {
-        if (!task_slow[t]) continue;  // chain_kernel already wrote this task's candidates
+    const uint32_t n_slow = slow_list[0];  // the tasks chain_kernel could not finish itself (usually none)
+    for (uint32_t k = blockIdx.x * (END_THREADS / 32) + warp; k < n_slow; k += warps_total) {
+        const uint32_t t = slow_list[1 + k];
         const int n = task_n[t];
         if (n == 0) continue;
         const uint32_t ch_k = desc[t].ch, cstart_k = desc[t].cstart;
-        const uint64_t *anc = anc_all + (size_t)t * MAXA;
-        const uint32_t *res = res_all + (size_t)t * MAXA;
+        const uint64_t *anc = anc_all + slab_base(t);  // entry i at [slab_off(i)]
+        const uint32_t *res = res_all + slab_base(t);
         uint32_t xs[MAXA / 32];
 #pragma unroll
         for (int u = 0; u < MAXA / 32; u++) {
             const int i = lane + 32 * u;
-            xs[u] = i < n ? __ldcg(res + i) : 0u;
+            xs[u] = i < n ? __ldcg(res + slab_off((uint32_t)i)) : 0u;
             if (i < n) bor[i] = 0;
         }
         __syncwarp();
@@ -542,7 +543,7 @@ ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_al
                 if ((mine >> u) & 1u) {
                     const int i = lane + 32 * u;
                     const uint32_t x = xs[u];
-                    const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + i);
+                    const uint64_t ar = __ldcg(anc + slab_off(rs_root(x))), ae = __ldcg(anc + slab_off((uint32_t)i));
                     Cand c;
                     c.q0 = cstart_k + an_q(ar);
                     c.q1 = cstart_k + an_q(ae);
@@ -580,8 +581,8 @@ ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_al
             int bi = -1;
             for (uint32_t mm = mine; mm; mm &= mm - 1) {
                 const int u = __ffs(mm) - 1, i = lane + 32 * u;
-                const uint32_t x = __ldcg(res + i);
-                const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + i);
+                const uint32_t x = __ldcg(res + slab_off((uint32_t)i));
+                const uint64_t ar = __ldcg(anc + slab_off(rs_root(x))), ae = __ldcg(anc + slab_off((uint32_t)i));
                 const uint32_t r0 = an_r(ar) < an_r(ae) ? an_r(ar) : an_r(ae);
                 const uint64_t key = ((uint64_t)(8191u - rs_f(x)) << 47) | ((uint64_t)an_q(ar) << 32) | (uint64_t)r0;
                 if (key < bk) {
@@ -594,8 +595,8 @@ ends_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_al
             const uint32_t klo = __reduce_min_sync(0xffffffffu, (uint32_t)(bk >> 32) == khi ? (uint32_t)bk : 0xffffffffu);
             if (bk == (((uint64_t)khi << 32) | klo)) {  // keys are unique: exactly one lane
                 mine &= ~(1u << ((bi - lane) >> 5));
-                const uint32_t x = __ldcg(res + bi);
-                const uint64_t ar = __ldcg(anc + rs_root(x)), ae = __ldcg(anc + bi);
+                const uint32_t x = __ldcg(res + slab_off((uint32_t)bi));
+                const uint64_t ar = __ldcg(anc + slab_off(rs_root(x))), ae = __ldcg(anc + slab_off((uint32_t)bi));
                 Cand c;
                 c.q0 = cstart_k + an_q(ar);
                 c.q1 = cstart_k + an_q(ae);

@@ -450,9 +450,10 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     PoolRef<Cand> b_cands(c->pool["ani.cands"]);
     PoolRef<PCand> b_pcands(c->pool["ani.pcands"]);
     PoolRef<uint32_t> b_task_pair(c->pool["ani.task_pair"]), b_cand_off(c->pool["ani.cand_off"]);
-    PoolRef<uint8_t> b_ncand(c->pool["ani.ncand"]), b_slow(c->pool["ani.slow"]);
-    b_anc.reserve((size_t)cap * MAXA + 2, 0, c->st);
-    b_res.reserve((size_t)cap * MAXA, 0, c->st);
+    PoolRef<uint8_t> b_ncand(c->pool["ani.ncand"]);
+    PoolRef<uint32_t> b_slow(c->pool["ani.slow_list"]);
+    b_anc.reserve(slab_entries(cap) + 2, 0, c->st);
+    b_res.reserve(slab_entries(cap), 0, c->st);
     b_tn.reserve((size_t)cap, 0, c->st);
     b_desc.reserve((size_t)cap, 0, c->st);
     b_cands.reserve((size_t)cap * SLOTS, 0, c->st);
@@ -460,7 +461,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
     b_task_pair.reserve((size_t)cap, 0, c->st);
     b_cand_off.reserve((size_t)cap + 1, 0, c->st);
     b_ncand.reserve((size_t)cap + 1, 0, c->st);
-    b_slow.reserve((size_t)cap, 0, c->st);
+    b_slow.reserve((size_t)cap + 1, 0, c->st);
     b_next.reserve(1, 0, c->st);
     b_fctl.reserve(4, 0, c->st);
     b_mid_list.reserve((size_t)cap_pairs, 0, c->st);
@@ -496,7 +497,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
         CK(cudaMemsetAsync(b_fctl.p, 0, 16, c->st));
         if (tasks) {
             CK(cudaMemsetAsync(b_ncand.p, 0, (size_t)tasks + 1, c->st));
-            CK(cudaMemsetAsync(b_slow.p, 0, (size_t)tasks, c->st));
+            CK(cudaMemsetAsync(b_slow.p, 0, 4, c->st));
             CK(cudaMemsetAsync(b_next.p, 0, 4, c->st));
             task_setup_kernel<<<nblk(tasks, 256), 256, 0, c->st>>>(view, d_info_s.p + bt.p0, c->d_task_off.p + bt.p0, base, np,
                                                                    tasks, b_desc.p, b_task_pair.p);
@@ -529,7 +530,7 @@ void run_ani(skb_ctx *c, const unsigned long long *d_pairs, int64_t n_pairs, Pai
                                                                                        b_cands.p, b_ncand.p, b_slow.p);
             CK(cudaGetLastError());
             if (trace) spans.push_back({"chain", bi, t0, mark()});
-            const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 32u);
+            const unsigned g3 = std::min<unsigned>(nblk(tasks, END_THREADS / 32), (unsigned)c->sm_count * 4u);
             ends_kernel<<<g3, END_THREADS, 0, c->st>>>(prm, tasks, b_anc.p, b_res.p, b_tn.p, b_desc.p, b_slow.p, b_cands.p,
                                                        b_ncand.p);
             CK(cudaGetLastError());

@@ -65,6 +65,15 @@ __host__ __device__ inline uint32_t rows_owned(uint32_t n, uint32_t part, uint32
 // following buckets behind a per-bucket flag (skb_probe.cuh).
 constexpr uint32_t BUCKET = 4;
 
+// Per-task scratch slabs of the pair stage (anchors: u64, DP results: u32): SLAB entries per task, contiguous.
+// (Round 2 tried interleaving the slabs of the 32 tasks a chain_kernel warp holds, in pieces of 4 entries, so that its
+// loads touch 8 lines instead of 32: chain_kernel did not move -- it is not bound by its loads -- and anchor_kernel,
+// whose warp-wide anchor stores then touch 8 lines instead of 2, went from 5.0 to 5.4 ms per batch.)
+constexpr int SLAB = 256;  // entries per task (= MAXA, skb_ani.cuh)
+__host__ __device__ inline size_t slab_base(uint32_t t) { return (size_t)t * SLAB; }
+__host__ __device__ inline uint32_t slab_off(uint32_t i) { return i; }
+__host__ __device__ inline size_t slab_entries(uint64_t tasks) { return (size_t)tasks * SLAB; }
+
 // Device view of the sketch DB (all pointers device memory)
 struct DbView {
     int32_t n_genomes;

@@ -209,7 +209,7 @@ __device__ __forceinline__ int probe_one(uint64_t sd, const Bucket &B, const uin
         if (c == 1) {
             const int dst = base + __popc(has & ((1u << lane) - 1u));
             const uint32_t v = enc_hit(e1, sd);
-            if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+            if (dst < max_anchors) __stcg(anc + slab_off((uint32_t)dst), ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
         }
         return base + __popc(has);
     }
@@ -225,13 +225,13 @@ __device__ __forceinline__ int probe_one(uint64_t sd, const Bucket &B, const uin
         if (c == 1) {
             const uint32_t v = enc_hit(e1, sd);
             if (base + pre < max_anchors)
-                __stcg(anc + base + pre, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+                __stcg(anc + slab_off((uint32_t)(base + pre)), ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
         }
     } else {
         for (int x = 0; x < c; x++) {
             const int dst = base + pre + x;
             const uint32_t v = stage[lane * STAGE_CAP + x];
-            if (dst < max_anchors) __stcg(anc + dst, ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
+            if (dst < max_anchors) __stcg(anc + slab_off((uint32_t)dst), ((uint64_t)(v >> 1) << 32) | lowbits | ((uint64_t)(v & 1u) << 16));
         }
     }
     return base + tot;
@@ -316,7 +316,7 @@ __device__ __forceinline__ int probe_narrow(uint2 sd, Bucket &B, const uint64_t 
         const int dst = base + __popc(has & ((1u << lane) - 1u));
         if (dst < max_anchors) {
             const uint32_t lo = (((sd.x >> 2) - cstart) << 17) | (((e ^ sd.x) & 1u) << 16) | (uint32_t)s;
-            __stcg(anc + dst, ((uint64_t)(e >> 2) << 32) | (uint64_t)lo);
+            __stcg(anc + slab_off((uint32_t)dst), ((uint64_t)(e >> 2) << 32) | (uint64_t)lo);
         }
     }
     return base + __popc(has);
