@@ -31,7 +31,11 @@
 namespace skb {
 
 constexpr int LB = 16;                        // DP look-back in anchors
-constexpr int DP_UNR = 4;                     // anchors per DP iteration (code size vs register moves)
+constexpr int DP_UNR = 4;                     // anchors fetched per DP iteration (one 32-byte sector)
+#ifndef SKB_DP_BODY
+#define SKB_DP_BODY 2
+#endif
+constexpr int DP_BODY = SKB_DP_BODY;          // copies of the DP step in the loop body (2 or 4): code size vs loop overhead
 constexpr int DIAG_SLACK = 64;                // chain_kernel short cut: diagonal drift followed without a rebuild
 constexpr int NEG_F = -(1 << 24);             // DP score of an empty window slot
 constexpr int ANC_THREADS = 256;              // K4a: 8 warps = 8 tasks per CTA pass
@@ -329,16 +333,20 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
 #pragma unroll
         for (int x = 0; x < UNR; x++) av[x] = vnext[x];
         if (i0 + UNR < MAXA) load4(i0 + UNR, vnext);  // next iteration's anchors
-        const int ring0 = (i0 & (LB - 1)) * DP_THREADS;  // slot of anchor i0; anchor i0 + x sits x slots further
-        uint32_t outp[UNR];
+        // The body is unrolled DP_BODY times (2), not UNR: at four copies the loop is 24 KB of code and 12 % of the
+        // kernel's stall samples were instruction fetches (ncu, round 2); the two halves of a group share one copy.
+#pragma unroll 1
+        for (int h = 0; h < UNR / DP_BODY; h++) {
+        const int ring0 = ((i0 + DP_BODY * h) & (LB - 1)) * DP_THREADS;  // slot of this half's first anchor
+        uint32_t outp[DP_BODY];
 #pragma unroll
-        for (int x = 0; x < UNR; x++) {
+        for (int x = 0; x < DP_BODY; x++) {
             const uint64_t a = av[x];
             const int rev = (int)an_rev(a);
             const int qi = (int)an_q(a) + (rev << 20);
             const int Ri = rev ? -(int)an_r(a) : (int)an_r(a);
             const int Di = Ri - qi;
-            const int i = i0 + x;
+            const int i = i0 + DP_BODY * h + x;
             int best = prm.anchor_score;
             uint32_t brc = (uint32_t)i << 9;  // own root, cnt 0 (+1 below)
             const bool live = i < my_n;
@@ -420,7 +428,17 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
             rf[ring0 + x * DP_THREADS] = FR1;
             off = ((off << 1) | (jump ? 1u : 0u)) & 0xffffu;
         }
-        if (i0 < my_n) __stcg(reinterpret_cast<uint4 *>(rp + slab_off((uint32_t)i0)), make_uint4(outp[0], outp[1], outp[2], outp[3]));
+        if (i0 + DP_BODY * h < my_n) {
+            if constexpr (DP_BODY == 4)
+                __stcg(reinterpret_cast<uint4 *>(rp + slab_off((uint32_t)i0)), make_uint4(outp[0], outp[1], outp[2], outp[3]));
+            else
+                __stcg(reinterpret_cast<uint2 *>(rp + slab_off((uint32_t)(i0 + DP_BODY * h))), make_uint2(outp[0], outp[1]));
+        }
+        if constexpr (DP_BODY == 2) {
+            av[0] = av[2];
+            av[1] = av[3];
+        }
+        }
     }
     // ---- the chunk's top candidates, by (score desc, q0, r0), into the task's slots
     if (my_n == 0) return;
