@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "skb_ani.cuh"
@@ -232,12 +233,13 @@ void exclusive_scan_u8(skb_ctx *c, const uint8_t *in, uint32_t *out, size_t n) {
     exclusive_scan_u32(c, out, out, n);
 }
 
-void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int end_bit = 64) {
+// stable LSD radix sort on key bits [begin_bit, end_bit)
+void sort_keys_u64(skb_ctx *c, const uint64_t *in, uint64_t *out, size_t n, int end_bit = 64, int begin_bit = 0) {
     size_t bytes = 0;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int64_t)n, 0, end_bit, c->st));
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int64_t)n, begin_bit, end_bit, c->st));
     c->d_tmp.reserve(bytes + 16, 0, c->st);
-    CK(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, bytes, in, out, (int64_t)n, 0, end_bit, c->st));
-    c->launches += (end_bit + 7) / 8 + 1;
+    CK(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, bytes, in, out, (int64_t)n, begin_bit, end_bit, c->st));
+    c->launches += (end_bit - begin_bit + 7) / 8 + 1;
 }
 
 // ---- sketch a batch of packed genomes [g0, g1) of the caller's list ------------------------------
@@ -985,26 +987,45 @@ static int index_impl(skb_ctx *c, bool tables_only) {
         tab_off.assign(n + 1, 0);
         tab_buckets.assign(n, 0);
         ctg_pstart.assign(c->h_ctg_len.size(), 0);
-        chunk_start.clear();
-        chunk_len.clear();
         c->h_chunk_off.assign(n + 1, 0);
+        // chunk counts first, then the tables are filled in place by a few host threads (1.5 M chunks at config3: the
+        // push_back loop this replaces was 4 ms of every index build, and is replicated on every rank)
+        const uint32_t CL = (uint32_t)c->prm.chunk_len;
         for (int32_t g = 0; g < n; g++) {
             const uint64_t ns = c->h_seed_off[g + 1] - c->h_seed_off[g];
             if (ns >= (1ull << 31)) return fail(c, SKB_ELIMIT, "genome has too many seeds");
             // a genome this context does not own is only ever a QUERY here: no table (skb_set_owned)
             tab_buckets[g] = c->owns(g) ? (uint32_t)std::max<uint64_t>(2, ns * (uint64_t)c->tab_x2 / 2 + 1) : 0u;
             tab_off[g + 1] = tab_off[g] + (uint64_t)tab_buckets[g] * BUCKET;
-            uint32_t off = 0;
-            for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
-                ctg_pstart[k] = off;
-                const uint32_t len = c->h_ctg_len[k];
-                for (uint32_t st = 0; st < len; st += (uint32_t)c->prm.chunk_len) {
-                    chunk_start.push_back(off + st);
-                    chunk_len.push_back(std::min<uint32_t>((uint32_t)c->prm.chunk_len, len - st));
+            uint64_t cnt = 0;
+            for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) cnt += (c->h_ctg_len[k] + CL - 1) / CL;
+            if ((uint64_t)c->h_chunk_off[g] + cnt >= (1ull << 32)) return fail(c, SKB_ELIMIT, "too many chunks");
+            c->h_chunk_off[g + 1] = c->h_chunk_off[g] + (uint32_t)cnt;
+        }
+        chunk_start.resize(c->h_chunk_off[n]);
+        chunk_len.resize(c->h_chunk_off[n]);
+        auto fill = [&](int32_t g0, int32_t g1) {
+            for (int32_t g = g0; g < g1; g++) {
+                uint32_t off = 0, at = c->h_chunk_off[g];
+                for (uint32_t k = c->h_ctg_off[g]; k < c->h_ctg_off[g + 1]; k++) {
+                    ctg_pstart[k] = off;
+                    const uint32_t len = c->h_ctg_len[k];
+                    for (uint32_t st = 0; st < len; st += CL, at++) {
+                        chunk_start[at] = off + st;
+                        chunk_len[at] = std::min<uint32_t>(CL, len - st);
+                    }
+                    off += len + CONTIG_PAD;
                 }
-                off += len + CONTIG_PAD;
             }
-            c->h_chunk_off[g + 1] = (uint32_t)chunk_start.size();
+        };
+        const int n_thr = n >= 1024 ? 4 : 1;
+        if (n_thr == 1)
+            fill(0, n);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; t++)
+                pool.emplace_back(fill, (int32_t)((int64_t)n * t / n_thr), (int32_t)((int64_t)n * (t + 1) / n_thr));
+            for (auto &th : pool) th.join();
         }
         lap("host tables");
         c->d_seed_off.upload(c->h_seed_off, c->st);
@@ -1066,7 +1087,10 @@ static int index_impl(skb_ctx *c, bool tables_only) {
             d_sorted.reserve(c->n_mkeys, 0, c->st);
             d_flag.reserve(c->n_mkeys + 1, 0, c->st);
             d_pos.reserve(c->n_mkeys + 1, 0, c->st);
-            sort_keys_u64(c, c->d_mkeys.p, d_sorted.p, c->n_mkeys);
+            // raw keys arrive genome by genome (ids ascending: skb_add_genomes, skb_import_sketches, skb_db_load), so a
+            // STABLE sort on the 42 marker bits alone leaves every marker's run ordered by genome id: 6 radix passes
+            // instead of 8
+            sort_keys_u64(c, c->d_mkeys.p, d_sorted.p, c->n_mkeys, 64, GID_BITS);
             unique_flag_kernel<<<nblk(c->n_mkeys, 256), 256, 0, c->st>>>(d_sorted.p, c->n_mkeys, d_flag.p);
             CK(cudaGetLastError());
             CK(cudaMemsetAsync(d_flag.p + c->n_mkeys, 0, 4, c->st));
@@ -1085,7 +1109,9 @@ static int index_impl(skb_ctx *c, bool tables_only) {
             c->d_markers.reserve(nu + 1, 0, c->st);
             swap_key_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_inv.p, nu, d_sorted.p);
             CK(cudaGetLastError());
-            sort_keys_u64(c, d_sorted.p, c->d_markers.p, nu);
+            // the input is ordered by marker: a stable sort on the 22 genome bits alone keeps each genome's markers
+            // ascending (3 passes instead of 8)
+            sort_keys_u64(c, d_sorted.p, c->d_markers.p, nu, 64, 2 * K_MARKER);
             strip_gid_kernel<<<nblk(nu, 256), 256, 0, c->st>>>(c->d_markers.p, nu);
             CK(cudaGetLastError());
             c->launches += 3;

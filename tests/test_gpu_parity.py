@@ -439,6 +439,22 @@ def test_device_edges_match_host_copy(eng7):
         assert np.array_equal(dev.cpu().numpy().view(EDGE_DTYPE), host)
 
 
+def test_general_and_narrow_pair_kernels_agree(eng7, monkeypatch):
+    """anchor_kernel / chain_kernel come in two variants: 32-bit record matching and diagonal arithmetic when every
+    padded position is below 2^30 (what any bacterial set runs), and the general one.  SKB_WIDE_DIAG=1 forces the
+    general variants: every integer and float of every pair must be identical."""
+    e, _ = eng7
+    pairs = list(itertools.combinations(range(7), 2)) + [(3, 1), (6, 0)]
+    a, b = [p[0] for p in pairs], [p[1] for p in pairs]
+    monkeypatch.delenv("SKB_WIDE_DIAG", raising=False)
+    narrow = e.pairs_detail(a, b)
+    monkeypatch.setenv("SKB_WIDE_DIAG", "1")
+    wide = e.pairs_detail(a, b)
+    key = lambda d: (d.swapped, d.n_chains, d.n_anchors, d.n_seeds, d.span_q, d.span_r, d.ani_raw, d.ani, d.af_a, d.af_b)
+    assert [key(d) for d in narrow] == [key(d) for d in wide]
+    assert any(d.n_chains > 0 for d in narrow)
+
+
 def test_full_size_genomes_against_oracle(oracle, built_lib):
     """BASELINE config-sized genomes (10 x 5 Mbp: two clades of 4 and two singletons) against the oracle, through the
     C-ABI: sketches bit-exact, prescreen decisions equal, pair integers exact, the 2-decimal edge list identical."""
