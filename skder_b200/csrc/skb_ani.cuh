@@ -280,13 +280,19 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
     // The look-back window beyond the two nearest predecessors: diagonal and packed (F, root, cnt) per entry, a ring in
     // shared memory ([slot][thread]: conflict-free, slot = anchor index & 15).  The query coordinate is not kept: the
     // only path that wants it (the full scan, ~0.6 % of the steps) re-reads it from the anchor array.
-    __shared__ int ringD[LB][DP_THREADS];
-    __shared__ uint32_t ringFR[LB][DP_THREADS];  // F << 17 | root << 9 | cnt  (0 = empty)
+    // Rows are padded by one word: the two uncommon paths read one task's COLUMN with 14 lanes at once (below), and rows
+    // DP_THREADS words apart would all fall into one bank.
+    constexpr int RS = DP_THREADS + 1;  // ring row stride in words
+    __shared__ int ringD[LB * RS];
+    __shared__ uint32_t ringFR[LB * RS];  // F << 17 | root << 9 | cnt  (0 = empty)
     __shared__ uint32_t tb_s[ENDS_K][DP_THREADS];  // dynamic indexing without local memory; column per thread
-    int *const rd = &ringD[0][threadIdx.x];
-    uint32_t *const rf = &ringFR[0][threadIdx.x];
+    int *const rd = &ringD[threadIdx.x];
+    uint32_t *const rf = &ringFR[threadIdx.x];
+    const int lane = threadIdx.x & 31;
+    const int *const rd_w = &ringD[threadIdx.x & ~31u];      // this warp's 32 columns: lane L's entry d at [slot * RS + L]
+    const uint32_t *const rf_w = &ringFR[threadIdx.x & ~31u];
 #pragma unroll
-    for (int u = 0; u < LB; u++) rf[u * DP_THREADS] = 0;
+    for (int u = 0; u < LB; u++) rf[u * RS] = 0;
     int Q1 = 0, D1 = 0, Q2 = 0, D2 = 0;  // nearest, second nearest predecessor
     uint32_t FR1 = 0, FR2 = 0;           // their ring words: (f + anchor_score) << 17 | root << 9 | cnt, 0 = none
     const uint32_t tt = t < n_tasks ? t : n_tasks - 1;  // idle lanes read a valid slab and write nothing
@@ -337,7 +343,7 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
         // kernel's stall samples were instruction fetches (ncu, round 2); the two halves of a group share one copy.
 #pragma unroll 1
         for (int h = 0; h < UNR / DP_BODY; h++) {
-        const int ring0 = ((i0 + DP_BODY * h) & (LB - 1)) * DP_THREADS;  // slot of this half's first anchor
+        const int ring0 = ((i0 + DP_BODY * h) & (LB - 1)) * RS;  // slot of this half's first anchor
         uint32_t outp[DP_BODY];
 #pragma unroll
         for (int x = 0; x < DP_BODY; x++) {
@@ -375,14 +381,29 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
                 const uint32_t window = 0xfffcu & ((1u << (i < LB ? i : LB)) - 1u);  // anchors i-3 .. i-16 that exist (all live)
                 int m2 = 0;
                 uint32_t offn = far ? window & ~off : 0u;  // `off` relative to this anchor's diagonal, beyond the nearest two
-                if (__any_sync(0xffffffffu, jump && !quick)) {
-#pragma unroll 1
-                    for (uint32_t todo = (jump && !quick) ? (far ? window & off : window) : 0u; todo; todo &= todo - 1) {
-                        const int d = __ffs((int)todo) - 1;
-                        const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
-                        const diff_t dd = adiff(rd[sl], Di);
-                        if (dd <= diag_lim) m2 = max(m2, (int)(rf[sl] >> 17));
-                        if (dd > DIAG_SLACK) offn |= 1u << d;
+                // The lanes that must look at their ring (a near jump, or a far one with flagged entries) are served
+                // one after the other by the whole warp: lane d reads entry d of that task's column, one max-reduction
+                // and one ballot give (m2, offn).  A per-lane loop here ran 14 iterations with one lane active --
+                // on genomes with repeat families (multi-hit seeds put several diagonals into one window) 19 % of the
+                // warp-steps did, and chain_kernel took 17.6 ms per batch instead of 3.9 (ncu, config3r).
+                const uint32_t my_todo = (jump && !quick) ? (far ? window & off : window) : 0u;
+                for (unsigned need = __ballot_sync(0xffffffffu, my_todo != 0u); need; need &= need - 1) {
+                    const int L = __ffs((int)need) - 1;
+                    const int DiL = __shfl_sync(0xffffffffu, Di, L);
+                    const uint32_t todoL = __shfl_sync(0xffffffffu, my_todo, L);
+                    int f_in = 0;
+                    bool off_in = false;
+                    if ((todoL >> lane) & 1u) {  // lane = d, 2 <= d < LB
+                        const int sl = ((i - 1 - lane) & (LB - 1)) * RS + L;
+                        const diff_t dd = adiff(rd_w[sl], DiL);
+                        if (dd <= diag_lim) f_in = (int)(rf_w[sl] >> 17);
+                        off_in = dd > DIAG_SLACK;
+                    }
+                    const int m2L = (int)__reduce_max_sync(0xffffffffu, (unsigned)f_in);
+                    const unsigned offL = __ballot_sync(0xffffffffu, off_in);
+                    if (lane == L) {
+                        m2 = m2L;
+                        offn |= offL;
                     }
                 }
                 if (jump) {
@@ -395,16 +416,35 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
                     }
                 }
             }
-            if (!__all_sync(0xffffffffu, settled)) {
-                if (!settled) {
-#pragma unroll 1
-                    for (int d = 2; d < LB; d++) {
-                        const int sl = ((i - 1 - d) & (LB - 1)) * DP_THREADS;
-                        const uint32_t fr = rf[sl];
-                        if (fr == 0) continue;  // empty slot (also: before the chunk's first anchor)
-                        const uint32_t lo = __ldcg(reinterpret_cast<const uint32_t *>(ap + slab_off((uint32_t)(i - 1 - d))));
-                        relax((int)((lo >> 17) & 0x7fffu) + (int)(((lo >> 16) & 1u) << 20) + 1, rd[sl], fr);
+            // Full scan of the window for the lanes the short cut could not settle, again one lane at a time with the
+            // warp's help: lane d relaxes against entry d (its query coordinate comes from the anchor array: the 14
+            // anchors are consecutive, one or two lines), the best candidate wins by one max-reduction on
+            // (cand << 4 | 15 - d): the largest candidate, ties to the nearest -- what the sequential scan gives.
+            for (unsigned need = __ballot_sync(0xffffffffu, !settled); need; need &= need - 1) {
+                const int L = __ffs((int)need) - 1;
+                const int DiL = __shfl_sync(0xffffffffu, Di, L), qiL = __shfl_sync(0xffffffffu, qi, L);
+                const int bestL = __shfl_sync(0xffffffffu, best, L);
+                const uint32_t ttL = __shfl_sync(0xffffffffu, tt, L);
+                uint32_t fr = 0, key = 0;
+                if (lane >= 2 && lane < LB && lane <= i - 1) {
+                    const int sl = ((i - 1 - lane) & (LB - 1)) * RS + L;
+                    fr = rf_w[sl];
+                    if (fr) {
+                        const uint32_t lo = __ldcg(reinterpret_cast<const uint32_t *>(
+                            anc_all + slab_base(ttL) + slab_off((uint32_t)(i - 1 - lane))));
+                        const int Qj = (int)((lo >> 17) & 0x7fffu) + (int)(((lo >> 16) & 1u) << 20) + 1;
+                        const int dq1 = qiL - Qj, dd = DiL - rd_w[sl], dr1 = dd + dq1;
+                        const int gap = dd < 0 ? -dd : dd;
+                        const int cand = (int)(fr >> 17) - gap;
+                        if ((unsigned)dq1 < band && dr1 >= 0 && gap <= prm.max_gap && cand > bestL)
+                            key = ((uint32_t)cand << 4) | (uint32_t)(LB - 1 - lane);
                     }
+                }
+                const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+                const uint32_t frs = __shfl_sync(0xffffffffu, fr, LB - 1 - (int)(kmax & 15u));
+                if (lane == L && kmax) {
+                    best = (int)(kmax >> 4);
+                    brc = frs & 0x1ffffu;
                 }
             }
             // the second nearest predecessor is beyond the nearest two of the next anchor
@@ -424,8 +464,8 @@ chain_kernel(AniParams prm, uint32_t n_tasks, const uint64_t *__restrict__ anc_a
             }
             Q2 = Q1, D2 = D1, FR2 = FR1;
             Q1 = qi + 1, D1 = Di, FR1 = live ? outp[x] + ((uint32_t)prm.anchor_score << 17) : 0u;
-            rd[ring0 + x * DP_THREADS] = D1;
-            rf[ring0 + x * DP_THREADS] = FR1;
+            rd[ring0 + x * RS] = D1;
+            rf[ring0 + x * RS] = FR1;
             off = ((off << 1) | (jump ? 1u : 0u)) & 0xffffu;
         }
         if (i0 + DP_BODY * h < my_n) {
