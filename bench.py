@@ -44,6 +44,7 @@ SKDER_ANI, SKDER_AF = 99.5, 50.0           # skDER's default cutoffs (bin/skder:
 # bounded sample the `cpu_baseline` leg of OUR arm is timed on (same generator): 80 clades x 5 members keeps the
 # workload's survivor fraction (1.0 % vs 0.98 %)
 CPU_SAMPLE_CLADES, CPU_SAMPLE_PER_CLADE = 80, 5
+SEARCH_BATCH_MAX = int(os.environ.get("SKB_SEARCH_BATCH", "32"))  # queries searched per call at most (1 = strictly one by one)
 SEARCH_WORKLOADS = ("config4", "tiny4")  # low_mem_greedy: the `skani sketch` + `skani search` path
 REF_BUDGET_S = float(os.environ.get("SKB_REF_BUDGET_S", "240"))  # wall budget of the reference arm's timed steps
 
@@ -210,15 +211,23 @@ def cpu_search_loop(workload, threads, n_clades, per_clade):
     sk, t_sketch = cpu_sketch_clades(workload, list(range(n_clades)), per_clade, threads)
     n = len(sk)
     order = sorted(range(n), key=lambda g: (-n50_of(sk[g].contig_lens()), g))
-    accounted, reps, t0 = set(), 0, time.perf_counter()
+    accounted, reps, rep_ids, t0 = set(), 0, [], time.perf_counter()
     for g in order:
         if g in accounted:
             continue
         reps += 1
+        rep_ids.append(g)
         for r, ani, af_r, af_q in O.search(sk, g, SEARCH_SCREEN / 100.0, SEARCH_MIN_AF / 100.0, threads):
             if round(ani * 100, 2) >= SKDER_ANI and round(af_q * 100, 2) >= SKDER_AF:  # skder.py:128 (col 4 = the query's AF)
                 accounted.add(r)
-    return {"n": n, "reps": reps, "t_sketch": t_sketch, "t_loop": time.perf_counter() - t0}
+    return {"n": n, "reps": reps, "t_sketch": t_sketch, "t_loop": time.perf_counter() - t0, "reps_sha256": ids_sha256(rep_ids)}
+
+
+def ids_sha256(ids):
+    """checksum of a set of workload-wide genome numbers (the representatives of a search loop)"""
+    import hashlib
+
+    return hashlib.sha256(np.sort(np.asarray(list(ids), np.int64)).tobytes()).hexdigest()
 
 
 def n50_of(lens):
@@ -719,13 +728,13 @@ def run_ours_search(args, torch, dist, rank, world, local):
             return
         head = torch.zeros(4, dtype=torch.int64, device=dev)
         if rank == owner:
+            mk0 = int(eng.sketch_view().n_marker_keys)  # this query's marker keys start here (earlier queries of the batch precede it)
             eng.add([packed[local_of[g]]])
             v = eng.sketch_view()
             so = np.ctypeslib.as_array(v.host_seed_off, shape=(n_db + 2,))
             co = np.ctypeslib.as_array(v.host_ctg_off, shape=(n_db + 2,))
             s0, ns = int(so[n_db]), int(so[n_db + 1] - so[n_db])
             nctg = int(co[n_db + 1] - co[n_db])
-            mk0 = add_query.mk_before
             nm = int(v.n_marker_keys) - mk0
             tl = int(np.ctypeslib.as_array(v.host_total_len, shape=(n_db + 1,))[n_db])
             head = torch.tensor([ns, nm, nctg, tl], dtype=torch.int64, device=dev)
@@ -758,36 +767,62 @@ def run_ours_search(args, torch, dist, rank, world, local):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         n_db = eng.n_genomes
-        add_query.mk_before = int(eng.sketch_view().n_marker_keys)
         all_db = np.arange(n_db, dtype=np.int32)
         accounted = np.zeros(n_full, bool)
-        reps = 0
-        for g in order:
-            if accounted[g]:
-                continue
-            reps += 1
-            add_query(g)
+        reps, rep_ids = 0, []
+        # The greedy loop is sequential, but a search result does not depend on the loop's state: the next K
+        # candidates in N50 order that are not accounted for YET are searched in one call (one index_append, one
+        # rectangle), and their results are applied in order -- a candidate an earlier one of the same batch accounts
+        # for is skipped exactly as the sequential loop would skip it, its result discarded ("speculation
+        # cannot change the answer").  K adapts: it doubles while nothing is discarded and halves when something is.
+        k_batch, pos, searched, wasted_all = 1, 0, 0, 0
+        while pos < n_full:
+            batch, p_ = [], pos
+            while p_ < n_full and len(batch) < k_batch:
+                if not accounted[order[p_]]:
+                    batch.append(order[p_])
+                p_ += 1
+            pos = p_
+            if not batch:
+                break
+            for g in batch:
+                add_query(g)
             try:
                 eng.index_append()
-                edges, st = eng.rect(all_db, [n_db], screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
+                edges, st = eng.rect(all_db, list(range(n_db, n_db + len(batch))), screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
             finally:
-                eng.pop_last_add()
+                for _ in batch:
+                    eng.pop_last_add()
+            searched += len(batch)
             # skder.py:128: ANI >= cutoff and the AF in column 4 (the query's) >= cutoff, on the printed 2-decimal values
             hit = (np.round(edges["ani"], 2) >= SKDER_ANI) & (np.round(edges["af_b"], 2) >= SKDER_AF)
+            qi = (edges["b"][hit].astype(np.int64) - n_db)
             ids = my_ids[edges["a"][hit]]
-            if world > 1:
-                cnt = torch.tensor([len(ids)], device=dev, dtype=torch.int64)
+            if world > 1:  # one exchange per batch: (query ordinal << 32 | workload-wide genome number) of every hit
+                rec = (qi << 32) | ids
+                cnt = torch.tensor([len(rec)], device=dev, dtype=torch.int64)
                 cnts = torch.zeros(world, device=dev, dtype=torch.int64)
                 dist.all_gather_into_tensor(cnts, cnt)
                 mx = max(int(cnts.max()), 1)
                 send = torch.full((mx,), -1, device=dev, dtype=torch.int64)
-                if len(ids):
-                    send[: len(ids)] = torch.from_numpy(ids).to(dev)
+                if len(rec):
+                    send[: len(rec)] = torch.from_numpy(rec).to(dev)
                 recv = torch.empty(world * mx, device=dev, dtype=torch.int64)
                 dist.all_gather_into_tensor(recv, send)
-                ids = recv[recv >= 0].cpu().numpy()
-            accounted[ids] = True
-            accounted[g] = True
+                rec = recv[recv >= 0].cpu().numpy()
+                qi, ids = rec >> 32, rec & 0xFFFFFFFF
+            wasted = 0
+            for j, g in enumerate(batch):
+                if accounted[g]:
+                    wasted += 1
+                    continue
+                reps += 1
+                rep_ids.append(g)
+                accounted[ids[qi == j]] = True
+                accounted[g] = True
+            wasted_all += wasted
+            k_batch = max(1, k_batch // 2) if wasted else min(SEARCH_BATCH_MAX, k_batch * 2)
+        one_run.searched, one_run.wasted, one_run.rep_ids = searched, wasted_all, rep_ids
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         return reps, reps * n_full, t1 - t0, t2 - t1, eng.launches - l0
@@ -821,7 +856,10 @@ def run_ours_search(args, torch, dist, rank, world, local):
             "config": {"workload": workload_name(args.workload) if nc == workload_shape(args.workload)[0] else
                        "%s, first %d clades only (%d genomes)" % (workload_name(args.workload), nc, n_full),
                        "representatives": reps, "searches": reps, "pairs": pairs, "searches_per_s": reps / t_loop,
-                       "ms_per_search": t_loop / reps * 1e3, "ms_sketch_index_db": float(np.mean([r[2] for r in res])) * 1e3,
+                       "ms_per_search": t_loop / reps * 1e3, "reps_sha256": ids_sha256(getattr(one_run, "rep_ids", [])),
+                       "search_batching": "up to %d candidates per call, %d searched, %d results discarded (candidate "
+                                          "accounted for by an earlier one of its batch)" % (
+                                              SEARCH_BATCH_MAX, getattr(one_run, "searched", reps), getattr(one_run, "wasted", 0)), "ms_sketch_index_db": float(np.mean([r[2] for r in res])) * 1e3,
                        "gen_s": t_gen,
                        "timing": "host clock between device synchronisations, max over ranks: the loop is sequential host "
                                  "logic around ~%d small launches per search" % max(1, launches // max(reps, 1)),

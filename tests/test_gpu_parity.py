@@ -601,7 +601,7 @@ def test_reference_sharded_triangle_single_process(eng7, ora7, oracle, genomes7,
             assert len(cat) < len(full) and set(map(tuple, cat[["a", "b"]].tolist())) < set(map(tuple, full[["a", "b"]].tolist()))
 
 
-def _bench_line(argv, nproc=1, timeout=900):
+def _bench_line(argv, nproc=1, timeout=900, env=None):
     import json
     import subprocess
     import sys
@@ -611,7 +611,7 @@ def _bench_line(argv, nproc=1, timeout=900):
     if nproc > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
                "--master-port", str(29900 + os.getpid() % 90), os.path.join(root, "bench.py")] + argv
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert out.returncode == 0 and lines, out.stdout[-1500:] + out.stderr[-3000:]
     return json.loads(lines[-1])
@@ -629,4 +629,8 @@ def test_search_loop_selects_what_the_oracle_loop_selects(built_lib, oracle):
     want = bench.cpu_search_loop("tiny4", 4, 4, 6)
     got = _bench_line(["--workload", "tiny4", "--steps", "1", "--warmup", "0"])
     assert got["config"]["representatives"] == want["reps"] and got["config"]["pairs"] == want["reps"] * want["n"]
+    assert got["config"]["reps_sha256"] == want["reps_sha256"]  # the same genomes, not just as many
     assert got["gpu_launches"] > 0
+    # the batched (speculative) loop and the strictly sequential one select the same representatives
+    seq = _bench_line(["--workload", "tiny4", "--steps", "1", "--warmup", "0"], env={"SKB_SEARCH_BATCH": "1"})
+    assert seq["config"]["reps_sha256"] == got["config"]["reps_sha256"]

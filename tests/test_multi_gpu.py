@@ -72,6 +72,7 @@ def test_two_gpu_search_loop_equals_single_gpu(built_lib):
     one = _bench_line(["--workload", "tiny4", "--steps", "1", "--warmup", "0"])
     two = _bench_line(["--workload", "tiny4", "--gpus", "2", "--steps", "1", "--warmup", "0"], nproc=2)
     assert two["n_gpus"] == 2 and two["config"]["representatives"] == one["config"]["representatives"]
+    assert two["config"]["reps_sha256"] == one["config"]["reps_sha256"]
 
 
 def test_two_gpu_bench_checksum_equals_single_gpu(built_lib):
