@@ -44,7 +44,7 @@ SKDER_ANI, SKDER_AF = 99.5, 50.0           # skDER's default cutoffs (bin/skder:
 # bounded sample the `cpu_baseline` leg of OUR arm is timed on (same generator): 80 clades x 5 members keeps the
 # workload's survivor fraction (1.0 % vs 0.98 %)
 CPU_SAMPLE_CLADES, CPU_SAMPLE_PER_CLADE = 80, 5
-SEARCH_BATCH_MAX = int(os.environ.get("SKB_SEARCH_BATCH", "32"))  # queries searched per call at most (1 = strictly one by one)
+SEARCH_BATCH_MAX = int(os.environ.get("SKB_SEARCH_BATCH", "64"))  # queries searched per call at most (1 = strictly one by one)
 SEARCH_WORKLOADS = ("config4", "tiny4")  # low_mem_greedy: the `skani sketch` + `skani search` path
 REF_BUDGET_S = float(os.environ.get("SKB_REF_BUDGET_S", "240"))  # wall budget of the reference arm's timed steps
 
