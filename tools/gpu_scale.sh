@@ -3,6 +3,7 @@ N=$1; shift
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then (timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -3) > gpurun_out/scale_tests_n$N.log; cat gpurun_out/scale_tests_n$N.log; fi
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 "$@" > gpurun_out/scale_n$N.log 2>&1
+grep '^{' gpurun_out/scale_n$N.log | tail -1 > gpurun_out/r2_bench_n$N.json
 python - $N <<'PY'
 import json,sys
 n=sys.argv[1]
