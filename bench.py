@@ -712,50 +712,13 @@ def run_ours_search(args, torch, dist, rank, world, local):
     pin, views, keep, h2d_bytes = pinned_views(packed, torch)
     arr = (C.POINTER(_lib.Packed) * len(views))(*[C.pointer(v) for v in views])
     eng = engine.Engine(local)
+    eng_q = engine.Engine(local) if world > 1 else None  # scratch context: this rank's share of a batch of queries
     dev = torch.device("cuda", local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def add_query(g):
-        """the query becomes genome n_db of every rank's context: sketched by its owner, imported by the others"""
-        owner = (g // per) % world
-        n_db = eng.n_genomes
-        if world == 1:
-            eng.add([packed[local_of[g]]])
-            return
-        head = torch.zeros(4, dtype=torch.int64, device=dev)
-        if rank == owner:
-            mk0 = int(eng.sketch_view().n_marker_keys)  # this query's marker keys start here (earlier queries of the batch precede it)
-            eng.add([packed[local_of[g]]])
-            v = eng.sketch_view()
-            so = np.ctypeslib.as_array(v.host_seed_off, shape=(n_db + 2,))
-            co = np.ctypeslib.as_array(v.host_ctg_off, shape=(n_db + 2,))
-            s0, ns = int(so[n_db]), int(so[n_db + 1] - so[n_db])
-            nctg = int(co[n_db + 1] - co[n_db])
-            nm = int(v.n_marker_keys) - mk0
-            tl = int(np.ctypeslib.as_array(v.host_total_len, shape=(n_db + 1,))[n_db])
-            head = torch.tensor([ns, nm, nctg, tl], dtype=torch.int64, device=dev)
-        dist.broadcast(head, src=owner)
-        ns, nm, nctg, tl = (int(x) for x in head.tolist())
-        buf = torch.empty(ns + nm + nctg, dtype=torch.int64, device=dev)
-        if rank == owner:
-            buf[:ns].copy_(multi._dev_tensor(torch, v.dev_seeds + 8 * s0, ns, dev))
-            # marker keys carry the sender's genome number in their low 22 bits: rebase to 0 for the receivers
-            buf[ns:ns + nm].copy_(multi._dev_tensor(torch, v.dev_marker_keys + 8 * mk0, nm, dev) - n_db)
-            cl = np.ctypeslib.as_array(v.host_ctg_len, shape=(int(v.n_contigs),))[int(co[n_db]):int(co[n_db + 1])]
-            buf[ns + nm:].copy_(torch.from_numpy(cl.astype(np.int64)))
-        dist.broadcast(buf, src=owner)
-        if rank != owner:
-            torch.cuda.current_stream(dev).synchronize()
-            cl = buf[ns + nm:].cpu().numpy().astype(np.uint32)
-            so = np.array([0, ns], np.uint64)
-            tls = np.array([tl], np.uint64)
-            co = np.array([0, nctg], np.uint32)
-            eng._ck(eng._L.skb_import_sketches(eng._h, 1, C.c_void_p(buf.data_ptr()), ns, C.c_void_p(buf.data_ptr() + 8 * ns), nm,
-                                               so.ctypes.data, tls.ctypes.data, co.ctypes.data, cl.ctypes.data, 0), "skb_import_sketches")
 
     def one_run():
         """sketch + index the shard, then the greedy loop; returns (reps, pairs, t_sketch, t_loop, launches)"""
@@ -785,18 +748,30 @@ def run_ours_search(args, torch, dist, rank, world, local):
             pos = p_
             if not batch:
                 break
-            for g in batch:
-                add_query(g)
+            if world == 1:
+                for g in batch:
+                    eng.add([packed[local_of[g]]])
+                ord_of_ctx, n_adds = np.arange(len(batch)), len(batch)
+            else:
+                # every rank sketches the candidates it holds into a scratch context; two small collectives bring all
+                # of them to every rank (rank-major); ord_of_ctx maps a query's place in the context back to its place
+                # in the batch (= N50 order)
+                own = [j for j, g in enumerate(batch) if (g // per) % world == rank]
+                eng_q.clear()
+                if own:
+                    eng_q.add([packed[local_of[batch[j]]] for j in own])
+                _, n_adds = multi.append_gathered_sketches(eng_q, eng, dist, torch)
+                ord_of_ctx = np.array([j for r in range(world) for j, g in enumerate(batch) if (g // per) % world == r], np.int64)
             try:
                 eng.index_append()
                 edges, st = eng.rect(all_db, list(range(n_db, n_db + len(batch))), screen=SEARCH_SCREEN, min_af=SEARCH_MIN_AF)
             finally:
-                for _ in batch:
+                for _ in range(n_adds):
                     eng.pop_last_add()
             searched += len(batch)
             # skder.py:128: ANI >= cutoff and the AF in column 4 (the query's) >= cutoff, on the printed 2-decimal values
             hit = (np.round(edges["ani"], 2) >= SKDER_ANI) & (np.round(edges["af_b"], 2) >= SKDER_AF)
-            qi = (edges["b"][hit].astype(np.int64) - n_db)
+            qi = ord_of_ctx[edges["b"][hit].astype(np.int64) - n_db]
             ids = my_ids[edges["a"][hit]]
             if world > 1:  # one exchange per batch: (query ordinal << 32 | workload-wide genome number) of every hit
                 rec = (qi << 32) | ids
@@ -863,8 +838,9 @@ def run_ours_search(args, torch, dist, rank, world, local):
                        "gen_s": t_gen,
                        "timing": "host clock between device synchronisations, max over ranks: the loop is sequential host "
                                  "logic around ~%d small launches per search" % max(1, launches // max(reps, 1)),
-                       "sharding": "database sharded N/P per rank; the query is sketched by the rank that holds it and its "
-                                   "sketch broadcast; hit ids all-gathered" if world > 1 else "one GPU holds the database"},
+                       "sharding": "database sharded N/P per rank; a batch's queries are sketched by the ranks that hold them, "
+                                   "their sketches all-gathered (two collectives per batch); hit ids all-gathered" if world > 1
+                                   else "one GPU holds the database"},
             "clocks": clk.summary(),
             "e2e": {"value": pairs / t_step, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_bytes) * world + reps * int(L // 4),
                     "d2h_bytes_per_step": int(32 * per * reps), "ms_per_step": t_step * 1e3,

@@ -50,18 +50,35 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
     if sharded_index and eng.n_genomes:
         eng.index_seed_tables()
     lap()
+    metas, gathered = _allgather_sketches(eng, dist, torch, lap)
+    eng.clear(keep_tables=sharded_index)
+    _import_gathered(eng, metas, gathered, keep_flags=sharded_index)
+    if sharded_index:
+        eng.set_owned(sum(int(m["n"]) for m in metas[:rank]), int(metas[rank]["n"]))
+    lap()
+    if prof and rank == 0:
+        sys.stderr.write("replicate: own index %.2f  meta %.2f  all-gather %.2f  import %.2f ms\n" % tuple(
+            (b - a) * 1e3 for a, b in zip(tm, tm[1:])))
+    return metas
+
+
+def _allgather_sketches(eng, dist, torch, lap=lambda: None):
+    """Raw sketches (seed records, marker keys) and host tables of every rank's context, all-gathered: returns
+    (metas per rank, [(seeds, stride), (marker keys, stride)] as padded device tensors)."""
     device = torch.device("cuda", eng.device)
     v = eng.sketch_view()
     n = v.n_genomes
-    meta = {
+    nctg = int(v.n_contigs)
+    meta = {  # an empty context (a rank without queries in this batch) has null host tables
         "n": n, "n_seeds": v.n_seeds, "n_mkeys": v.n_marker_keys,
-        "seed_off": np.ctypeslib.as_array(v.host_seed_off, shape=(n + 1,)).copy(),
-        "total_len": np.ctypeslib.as_array(v.host_total_len, shape=(max(n, 1),))[:n].copy(),
-        "ctg_off": np.ctypeslib.as_array(v.host_ctg_off, shape=(n + 1,)).copy(),
-        "ctg_len": np.ctypeslib.as_array(v.host_ctg_len, shape=(max(int(v.n_contigs), 1),))[: int(v.n_contigs)].copy(),
+        "seed_off": np.ctypeslib.as_array(v.host_seed_off, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64),
+        "total_len": np.ctypeslib.as_array(v.host_total_len, shape=(n,)).copy() if n else np.zeros(0, np.uint64),
+        "ctg_off": np.ctypeslib.as_array(v.host_ctg_off, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint32),
+        "ctg_len": np.ctypeslib.as_array(v.host_ctg_len, shape=(nctg,)).copy() if nctg else np.zeros(0, np.uint32),
     }
-    metas = _exchange_meta(meta, dist, torch, torch.device("cuda", eng.device) if dist.get_backend() == "nccl" else None)
+    metas = _exchange_meta(meta, dist, torch, device if dist.get_backend() == "nccl" else None)
     lap()
+    world = dist.get_world_size()
     gathered = []
     for key, ptr, cnt in (("n_seeds", v.dev_seeds, v.n_seeds), ("n_mkeys", v.dev_marker_keys, v.n_marker_keys)):
         mx = max(int(m[key]) for m in metas)
@@ -73,8 +90,13 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
         gathered.append((recv, max(mx, 1)))
     torch.cuda.synchronize(device)
     lap()
-    eng.clear(keep_tables=sharded_index)
+    return metas, gathered
+
+
+def _import_gathered(eng, metas, gathered, keep_flags=False):
+    """Append every rank's gathered sketches to `eng`, rank-major; returns the number of import (= add) calls made."""
     (seeds, s_stride), (mkeys, m_stride) = gathered
+    calls = 0
     for r, m in enumerate(metas):
         if m["n"] == 0:
             continue
@@ -86,16 +108,19 @@ def replicate_sketches(eng, dist, torch, sharded_index=False):
             eng._L.skb_import_sketches(
                 eng._h, int(m["n"]), C.c_void_p(seeds.data_ptr() + 8 * r * s_stride), int(m["n_seeds"]),
                 C.c_void_p(mkeys.data_ptr() + 8 * r * m_stride), int(m["n_mkeys"]), so.ctypes.data, tl.ctypes.data,
-                co.ctypes.data, cl.ctypes.data, 1 if sharded_index else 0),
+                co.ctypes.data, cl.ctypes.data, 1 if keep_flags else 0),
             "skb_import_sketches",
         )
-    if sharded_index:
-        eng.set_owned(sum(int(m["n"]) for m in metas[:rank]), int(metas[rank]["n"]))
-    lap()
-    if prof and rank == 0:
-        sys.stderr.write("replicate: own index %.2f  meta %.2f  all-gather %.2f  import %.2f ms\n" % tuple(
-            (b - a) * 1e3 for a, b in zip(tm, tm[1:])))
-    return metas
+        calls += 1
+    return calls
+
+
+def append_gathered_sketches(src, dst, dist, torch):
+    """Search path: every rank sketched its share of a batch of query genomes into the scratch context `src`; all of
+    them are appended to `dst` on every rank, rank-major (two small collectives per batch instead of two broadcasts per
+    query).  Returns (metas per rank, number of add calls to pop afterwards).  Collective: all ranks must call."""
+    metas, gathered = _allgather_sketches(src, dist, torch)
+    return metas, _import_gathered(dst, metas, gathered, keep_flags=False)
 
 
 def _exchange_meta(meta, dist, torch, device):
