@@ -5,23 +5,25 @@
 // spans, chain count) are bit-exact against oracle/skani_oracle.c ora_pair(); ANI/AF are the same
 // IEEE double expressions (device pow() may differ from glibc's in the last ulp).
 //
-// A task = (surviving pair, 20 kb query chunk).  Three kernels, each at the occupancy its bottleneck
-// wants; anchors and DP results go through a scratch array in HBM (written once, read once: the
-// 2*16*A term of the roofline model).
-//   K4a anchor_kernel (warp per task, many warps/SM): streams the chunk's position-ordered seeds
-//      (coalesced 8-byte records), probes the reference's bucketed hash index (L2-resident: a
-//      clade's members all hit the same tables) and writes the anchors in QUERY order -- the order
-//      the DP wants, so there is no sort.
-//   K4b chain_kernel (thread per task): the chaining DP with its 16-anchor look-back window in
-//      registers; no shuffles, no shared memory, ~11 instructions per (anchor, predecessor), 32 tasks
-//      per warp instruction.
-//   K4c ends_kernel (warp per task): best end of every DP tree with >= min_anchors / min_score; the
-//      chunk's top `max_chunk_chains` by (score, q0, r0) go to the task's fixed candidate slots.
-// finalize_kernel: one CTA per pair gathers the candidates, orders them by (score desc, chunk,
-//   ordinal), resolves the greedy non-overlap selection in parallel rounds, sums anchors, seeds and the
-//   symmetrically clipped spans of the accepted chains, and reduces ANI = ((A - 2n) / (S - 2n))^(1/15) (n chains,
-//   end anchors left out), AF = span / genome length.  Pairs with more than MAXP candidates run the same code on
-//   global scratch (finalize_kernel<true>).
+// A task = (surviving pair, 20 kb query chunk).  Kernels, each at the occupancy its bottleneck wants; anchors and
+// DP results go through a scratch array in HBM (written once, read once: the 2*16*A term of the roofline model).
+//   K4a anchor_kernel (warp per task, 3 CTAs of 8 warps per SM, tasks grabbed 8 at a time): streams the chunk's
+//      position-ordered seeds (coalesced 8-byte records), probes the reference's bucketed hash index (L2-resident: a
+//      clade's members all hit the same tables) and writes the anchors in QUERY order -- the order the DP wants, so
+//      there is no sort.  Bound by the L1 data pipe: every lookup is one scattered 32-byte sector.
+//   K4b chain_kernel (thread per task): the chaining DP.  The two nearest predecessors live in registers, the rest
+//      of the 16-anchor look-back window in a shared-memory ring that only the two uncommon paths read -- and those
+//      are served by the whole warp (lane d takes window entry d).  It also tracks the best end of every DP tree and
+//      writes the chunk's top candidates itself.
+//   K4c ends_kernel (warp per task): the chunks with more DP trees than chain_kernel tracks (a compact list): best
+//      end of every tree with >= min_anchors / min_score; the chunk's top `max_chunk_chains` by (score, q0, r0).
+//   cand_pack_kernel + finalize_warp_kernel: chains packed into per-pair lists (extension precomputed); ONE WARP per
+//      pair orders them, finds the chains that touch, resolves the greedy non-overlap selection over those only, sums
+//      anchors, seeds and the symmetrically clipped spans of the accepted chains, and writes
+//      ANI = ((A - 2n) / (S - 2n))^(1/15) (n chains, end anchors left out), AF = span / genome length.
+//   finalize_kernel: one CTA per pair, for the pairs the warp kernel lists (more candidates than its shared memory
+//      takes, or many blocking relations); beyond MAXP candidates the same code runs on global scratch
+//      (finalize_kernel<true>).  No pair is capped or dropped.
 #pragma once
 #include <type_traits>
 

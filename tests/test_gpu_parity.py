@@ -185,6 +185,8 @@ def test_skani_shim_triangle_dist_search_bytes_equal_oracle(genomes7, oracle, bu
     out = tmp_path / "Skani_Triangle_Edge_Output.txt"
     assert _run_shim(["triangle", "-l", str(lst), "--min-af", "50.0", "-E", "-s", "89.0", "-t", "4", "-o", str(out)]) == 0
     assert out.read_text() == skani_cpu.triangle_tsv(genomes7, 89.0, 50.0, threads=4)
+    # provenance beside the output: skDER discards stdout/stderr, and the numbers are not the skani binary's
+    assert "NOT the skani binary" in (tmp_path / (out.name + ".skani_b200.log")).read_text()
     # dist: reps vs non-reps, no -t, default screen / min-af
     rl, ql = tmp_path / "Reps_Listing.txt", tmp_path / "NonReps_Listing.txt"
     rl.write_text("".join(p + "\n" for p in genomes7[:4]))
