@@ -188,3 +188,69 @@ def test_packer_line_shapes_against_plain_python(built_lib, tmp_path):
             assert not np.any(w[(len(codes) + 31) // 32:])  # padding words are zero
             if len(codes) % 32:
                 assert int(w[len(codes) // 32]) >> (2 * (len(codes) % 32)) == 0  # and so are the unused bits
+
+
+def test_bench_host_helpers_without_a_gpu():
+    """Host-side pieces of bench.py / multi.py that must not need a device: the clock sampler degrades to
+    "unsampled" instead of raising, the NUMA binding says None where sysfs or the GPU is missing, and the checksum of
+    a representative set does not depend on the order the loop found them in."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+
+    from skder_b200 import multi
+
+    assert bench.ids_sha256([5, 1, 9]) == bench.ids_sha256([9, 5, 1]) != bench.ids_sha256([5, 1])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert multi.bind_to_gpu_numa_node(torch, 0) is None
+    with bench.ClockSampler(0) as clk:
+        pass
+    s = clk.summary()
+    assert s["sm_mhz"] is None and s["reasons"] == ["unsampled"]
+
+
+def test_speculative_search_loop_is_the_sequential_loop():
+    """bench.py's config4 loop searches the next K unaccounted candidates in one call and applies the results in N50
+    order, skipping a candidate an earlier one of its batch accounted for (reference loop: src/skDER/skder.py:116-133).
+    Model of that control flow on random hit sets: the representatives equal the one-by-one loop's for every K."""
+    rng = np.random.default_rng(7)
+    n = 300
+    clade = rng.integers(0, 40, n)
+    # hits of a query: a random subset of its clade (state-independent, like a search result)
+    hits = [np.flatnonzero((clade == clade[g]) & (rng.random(n) < 0.6)) for g in range(n)]
+    order = rng.permutation(n).tolist()
+
+    def sequential():
+        acc, reps = np.zeros(n, bool), []
+        for g in order:
+            if acc[g]:
+                continue
+            reps.append(g)
+            acc[hits[g]] = True
+            acc[g] = True
+        return reps
+
+    def batched(kmax):
+        acc, reps, k, pos = np.zeros(n, bool), [], 1, 0
+        while pos < n:
+            batch, p = [], pos
+            while p < n and len(batch) < k:
+                if not acc[order[p]]:
+                    batch.append(order[p])
+                p += 1
+            pos = p
+            wasted = 0
+            for g in batch:
+                if acc[g]:
+                    wasted += 1
+                    continue
+                reps.append(g)
+                acc[hits[g]] = True
+                acc[g] = True
+            k = max(1, k // 2) if wasted else min(kmax, k * 2)
+        return reps
+
+    want = sequential()
+    for kmax in (1, 2, 7, 64):
+        assert batched(kmax) == want
