@@ -215,6 +215,8 @@ def run_search(opt, engine_mod):
         if not rep.get("ok"):
             raise RuntimeError("search daemon: %s" % rep.get("error"))
         return None
+    if engine_mod is None:
+        from . import engine as engine_mod
     query = opt["positional"][0]
     with open(os.path.join(opt["db"], "manifest.json")) as f:
         man = json.load(f)
@@ -264,7 +266,12 @@ def main(argv=None):
         if "-o" in argv[:-1]:
             out_hint = argv[argv.index("-o") + 1]
         sub, opt = parse_args(argv)
-        from . import engine as engine_mod  # loads libskani_b200.so; raises if missing (no CPU path)
+        # A `search` the database's daemon answers needs neither numpy nor the CUDA library in THIS process: skDER's
+        # low_mem_greedy loop launches one `skani search` per representative (src/skDER/skder.py:116-120), and importing
+        # the engine costs ~0.5 s a time against ~0.1 s for the interpreter plus the socket client.
+        engine_mod = None
+        if not (sub == "search" and os.environ.get("SKB_NO_DAEMON") != "1"):
+            from . import engine as engine_mod  # loads libskani_b200.so; raises if missing (no CPU path)
 
         {"triangle": run_triangle, "sketch": run_sketch, "search": run_search, "dist": run_dist}[sub](opt, engine_mod)
         _provenance(opt, sub, time.time() - t0)

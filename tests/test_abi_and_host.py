@@ -254,3 +254,56 @@ def test_speculative_search_loop_is_the_sequential_loop():
     want = sequential()
     for kmax in (1, 2, 7, 64):
         assert batched(kmax) == want
+
+
+def test_search_through_a_running_daemon_loads_neither_numpy_nor_the_engine(tmp_path):
+    """skDER's low_mem_greedy loop launches one `skani search` process per representative (reference
+    src/skDER/skder.py:116-120).  When the database's daemon answers, the client process must stay light: no numpy,
+    no libskani_b200.so.  A stand-in server speaks the daemon's protocol (authenticated Unix socket, JSON bytes)."""
+    import json
+    import threading
+    from multiprocessing.connection import Listener
+
+    from skder_b200 import daemon
+
+    db = tmp_path / "skani_sketch_all.db"
+    db.mkdir()
+    env = dict(os.environ, SKB_DAEMON_DIR=str(tmp_path), SKB_DEVICE="0", PYTHONPATH=ROOT)
+    env.pop("SKB_NO_DAEMON", None)
+    os.environ["SKB_DAEMON_DIR"] = str(tmp_path)
+    try:
+        sock = daemon.socket_path(str(db), 0)
+    finally:
+        os.environ.pop("SKB_DAEMON_DIR", None)
+    key = b"k" * 32
+    with open(daemon._key_path(str(db), 0), "wb") as f:
+        f.write(key)
+    seen = []
+
+    def serve():
+        with Listener(sock, family="AF_UNIX", authkey=key) as ls:
+            with ls.accept() as conn:
+                msg = json.loads(conn.recv_bytes().decode())
+                seen.append(msg)
+                with open(msg["out"], "w") as f:
+                    f.write("header\n")
+                conn.send_bytes(json.dumps({"ok": True}).encode())
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    for _ in range(200):
+        if os.path.exists(sock):
+            break
+        import time
+
+        time.sleep(0.01)
+    out = tmp_path / "current_search_results.tsv"
+    code = ("import sys; from skder_b200.cli import main; rc = main(sys.argv[1:]); "
+            "print('numpy' in sys.modules, 'skder_b200.engine' in sys.modules, rc)")
+    r = subprocess.run([sys.executable, "-c", code, "search", "query.fa", "-d", str(db), "-o", str(out), "-t", "4"],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=60)
+    th.join(timeout=10)
+    assert r.stdout.split() == ["False", "False", "0"], r.stdout + r.stderr
+    assert out.read_text() == "header\n"
+    assert seen and seen[0]["op"] == "search" and seen[0]["query"] == str(tmp_path / "query.fa") and seen[0]["label"] == "query.fa"
+    assert "NOT the skani binary" in (tmp_path / "current_search_results.tsv.skani_b200.log").read_text()
