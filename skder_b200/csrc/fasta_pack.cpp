@@ -313,9 +313,8 @@ int skb_pack_contigs(const char *const *seqs, const int64_t *lens, int32_t n, in
     for (int32_t i = 0; i < n; i++) {
         all_lens.push_back(lens[i]);
         if (lens[i] < min_contig_len || lens[i] <= 0) continue;
-        kept.push_back(lens[i]);
         const uint8_t *s = (const uint8_t *)seqs[i];
-        for (int64_t j = 0; j < lens[i]; j++) pk.put(kCode.t[s[j]] & 3);  // every byte is a base here (no blank handling)
+        kept.push_back(pk.put_line(s, lens[i], s + lens[i]));  // the whole contig as one line (blanks, if any, are dropped)
     }
     *out = make_packed(pk, kept, "", all_lens);
     return *out ? SKB_OK : SKB_ENOMEM;
