@@ -52,8 +52,13 @@ def run_skder(genome_dir_or_files, outdir, mode="greedy", ani=99.0, af=50.0, thr
     if clusters:
         cmd.append("-n")
     cmd += list(extra)
+    # the reference writes Skani_Dist_Output.txt RELATIVE to its working directory (bin/skder:468): run it beside its
+    # output directory, not wherever the caller happens to be (only when every path given is absolute)
+    work = os.path.dirname(os.path.abspath(outdir.rstrip("/")))
+    movable = os.path.isabs(outdir) and all(os.path.isabs(x) for x in g) and os.path.isdir(work)
     t0, w0 = time.perf_counter(), time.time()
-    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
+                       cwd=work if movable else None)
     wall = time.perf_counter() - t0
     out = outdir if outdir.endswith("/") else outdir + "/"
     run_skder.last_phases = phases_from_files(out, w0, time.time())
